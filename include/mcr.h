@@ -1,0 +1,256 @@
+/*
+ * mcr.h — C ABI of the B200-native Monte Carlo retirement path engine (libmcr_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of rflamino/monte_carlo_retirement: the
+ * per-path timeline engine, its batch aggregations and the working-months search of
+ * `backend/simulation.py`. The reference has no FFI today (it is pure Python), so every entry
+ * point below cites the reference interface it replaces (file:line relative to the reference
+ * root). The host-side mirror that binds these with ctypes is
+ * `monte_carlo_retirement_b200/simulation.py`; INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MCR_E* code otherwise; the message is
+ *     available through mcr_last_error(ctx) (thread-local when ctx == NULL);
+ *   - no exceptions, no torch types: plain pointers and sizes. Pointers named *_dev are DEVICE
+ *     pointers owned by the caller (the Python side gets them from torch.Tensor.data_ptr());
+ *     pointers named *_host are host pointers. The library never frees caller memory and never
+ *     returns memory it allocated, only fills caller buffers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); all work
+ *     is enqueued on it and the call returns without synchronising unless it fills a *_host
+ *     output;
+ *   - one mcr_ctx per simulator instance; a context is bound to one CUDA device and may be used
+ *     from any host thread, one call at a time (calls on one context are serialised
+ *     internally). There is no global mutable state, so concurrent contexts are safe
+ *     (reference callers: worker threads of `backend/server.py:309,405`).
+ *   - there is NO CPU fallback: every compute entry point fails with MCR_ECUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef MCR_H_
+#define MCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCR_ABI_VERSION 1
+#define MCR_MAX_STREAMS 16      /* other_income_streams is unbounded in the reference
+                                   (backend/config.py:99); more than this -> MCR_EINVAL */
+#define MCR_MONTHS_PER_YEAR 12  /* backend/constants.py:1 */
+#define MCR_SMALL_EPSILON 1e-6  /* backend/constants.py:3 */
+
+/* error codes */
+#define MCR_OK 0
+#define MCR_EINVAL (-1)   /* bad argument: Python shim raises ValueError   */
+#define MCR_ECUDA (-2)    /* CUDA runtime / launch error: RuntimeError     */
+#define MCR_ENOMEM (-3)   /* scratch allocation failed: RuntimeError       */
+
+/* flags for mcr_simulate / mcr_replay / mcr_search_batch */
+#define MCR_FLAG_STRICT 0x1u /* reference operation order, no FMA contraction, no reciprocal
+                                sharing: the parity build. Replay and single-path runs always
+                                use it. Without it the fast arithmetic is used (same
+                                formulas, FMA contraction + shared reciprocals, <=1e-12 rel). */
+
+/* seed streams — backend/simulation.py:147-151,177-185 (search vs final SeedSequence children) */
+#define MCR_STREAM_SEARCH 0
+#define MCR_STREAM_FINAL 1
+
+/* One `other_income_streams` entry — backend/config.py:12-47 (OtherIncomeStreamConfig). */
+typedef struct mcr_income_stream {
+  double monthly_amount_today;
+  double start_at_age;
+  double tax_rate;
+  int32_t duration_years;    /* -1 == None (paid indefinitely)                          */
+  int32_t inflation_indexed; /* 0/1                                                      */
+} mcr_income_stream;
+
+/*
+ * Flattened scenario — backend/config.py:48-126 (Config) plus the three lognormal parameter
+ * pairs the simulator derives at construction (backend/simulation.py:156-166,
+ * arithmetic_to_log_params :14-29). The log parameters are computed by the HOST caller with the
+ * reference's own formula so that the constants the kernel sees equal the reference's bit for
+ * bit (log/sqrt are not re-evaluated on the device).
+ */
+typedef struct mcr_params {
+  double initial_balance;
+  double monthly_contribution;
+  double contribution_growth_rate_annual;
+  double monthly_expenses;
+  double current_age;
+  double allocation_inv1_pct;
+  double inv1_mu_log, inv1_sigma_log; /* equity                      */
+  double inf_mu_log, inf_sigma_log;   /* inflation                   */
+  double prem_mu_log, prem_sigma_log; /* inv2 premium over inflation */
+  double equity_inflation_rho;
+  double inv1_annual_tax_on_gains_rate;
+  double inv1_realized_gains_tax_rate;
+  double inv2_annual_tax_on_gains_rate;
+  double inv2_realized_gains_tax_rate;
+  int32_t inv1_use_realized_gains_tax_system;
+  int32_t inv2_use_realized_gains_tax_system;
+  int32_t retirement_years;
+  int32_t n_streams;
+  mcr_income_stream streams[MCR_MAX_STREAMS];
+} mcr_params;
+
+/*
+ * Per-path outputs of one batch — replaces the list of 10-key dicts that
+ * `_run_single_simulation_path` returns (backend/simulation.py:939-950) and that
+ * `run_monte_carlo_simulations` turns into `summary_df` and the three series frames
+ * (:1012-1038,1099-1103). All pointers are DEVICE pointers, any of them may be NULL (that
+ * output is then not produced). Column layout is structure-of-arrays; the series are
+ * time-major so that a warp's 32 paths store 256 contiguous bytes:
+ *   trajectory[t * ld + i]   t in [0, T),  T = 1 + ceil(working_months/12) + retirement_years
+ *   wr[y * ld + i]           y in [0, retirement_years)
+ * with i the path's index inside this batch and ld >= n_paths (`series_ld`).
+ */
+typedef struct mcr_outputs {
+  double* start_balance;      /* "Start Balance"                         */
+  double* final_balance;      /* "Final Balance" (clamped >= 0)          */
+  uint8_t* success;           /* "Success" 0/1                           */
+  int32_t* ruin_month;        /* "YearsToRuin" * 12, -1 == NaN (success) */
+  double* first_year_gross;   /* "First Year Gross Withdrawal"           */
+  double* first_year_real;    /* "First Year Real Gross Withdrawal"      */
+  double* inflation_at_ret;   /* "Inflation At Retirement"               */
+  double* trajectory;         /* "Trajectory"      [T][ld]               */
+  double* real_trajectory;    /* "RealTrajectory"  [T][ld]               */
+  double* wr_trajectory;      /* "WithdrawalRateTrajectory" [R][ld], NaN = no observation */
+  int64_t series_ld;          /* leading dimension of the three series   */
+  /* device-side reductions (each may be NULL) */
+  int64_t* success_count;     /* [1]  += number of successful paths (a15, :1130-1136)      */
+  int64_t* wr_obs_count;      /* [R]  += non-NaN WR observations per year (:1111-1113)     */
+  int64_t* ruin_month_hist;   /* [12R+1] += failed paths per ruin month (server.py:525-532)*/
+  uint64_t* executed_months;  /* [1]  += months actually stepped (roofline accounting)     */
+} mcr_outputs;
+
+/* Host record of one path — the scalar part of the dict at backend/simulation.py:939-950. */
+typedef struct mcr_path_record {
+  double start_balance;
+  double final_balance;
+  double first_year_gross;
+  double first_year_real;
+  double inflation_at_ret;
+  int32_t success;
+  int32_t ruin_month; /* -1 == NaN */
+  int32_t trajectory_len;
+  int32_t wr_len;
+} mcr_path_record;
+
+typedef struct mcr_ctx mcr_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Replaces RetirementMonteCarloSimulator.__init__ (backend/simulation.py:135-175): validates
+ * and freezes the scenario, derives the Philox key from main_seed, binds to `device`. */
+int mcr_create(const mcr_params* params, uint64_t main_seed, int device, mcr_ctx** out_ctx);
+int mcr_destroy(mcr_ctx* ctx);
+const char* mcr_last_error(const mcr_ctx* ctx);
+int mcr_abi_version(void);
+
+/* ---- host-side pure helpers (a2/a3 of SURVEY §8) -------------------------------------- */
+
+/* stream_payment_start_month_index (backend/simulation.py:47-63). */
+int32_t mcr_stream_start_month(double current_age, int32_t working_months, double start_at_age);
+/* Number of yearly trajectory points, 1 + ceil(wm/12) + R (backend/simulation.py:585-589,902). */
+int32_t mcr_trajectory_len(int32_t working_months, int32_t retirement_years);
+
+/* ---- the timeline kernel -------------------------------------------------------------- */
+
+/* Native-RNG batch: replaces the fan-out of run_monte_carlo_simulations
+ * (backend/simulation.py:973-1010) — `_path_seeds` (:187-199) + n x
+ * `_run_single_simulation_path` (:476-950) with `_draw_shock_path` (:452-466) replaced by
+ * counter-based Philox4x32-10 keyed by (main_seed, seed_stream) and counted by
+ * (first_path + i, absolute month). Path i of this call is GLOBAL path first_path + i, so
+ * shards of one run on several GPUs draw disjoint subsequences and the result of a path does
+ * not depend on the shard layout or on working_months (common random numbers). */
+int mcr_simulate(mcr_ctx* ctx, int seed_stream, int32_t working_months, int64_t first_path,
+                 int64_t n_paths, uint32_t flags, const mcr_outputs* out, void* stream);
+
+/* Replay batch: same kernel body fed with precomputed correlated shocks (the reference's own
+ * numpy draws, backend/simulation.py:452-466), device layout shocks_dev[(m*3 + c) * shocks_ld
+ * + i], m in [0, n_months), c in {equity, inflation, premium}. n_months must be
+ * >= max(working_months + 12R, 1). Always strict arithmetic. */
+int mcr_replay(mcr_ctx* ctx, const double* shocks_dev, int64_t shocks_ld, int32_t n_months,
+               int32_t working_months, int64_t n_paths, const mcr_outputs* out, void* stream);
+
+/* One path from HOST shocks[n_months][3] (row-major, as `_draw_shock_path` returns) to HOST
+ * outputs: replaces a direct call of `_run_single_simulation_path`
+ * (backend/simulation.py:476-950; 11 reference tests call it). Runs the strict kernel with one
+ * thread on the device and synchronises. trajectory/real_trajectory need trajectory_len
+ * doubles, wr needs retirement_years doubles (may be NULL). */
+int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_host,
+                    int32_t n_months, mcr_path_record* record_host, double* trajectory_host,
+                    double* real_trajectory_host, double* wr_host);
+
+/* Device evaluation of the three private helpers the reference tests call directly
+ * (backend/simulation.py:201-254, :256-272, :274-359). One strict thread each. */
+int mcr_helper_withdraw(mcr_ctx* ctx, double bal, double cost_basis, double net_target,
+                        int32_t use_real_tax, double real_tax_rate, double out4_host[4]);
+int mcr_helper_net_liquidation(mcr_ctx* ctx, double bal, double cost_basis, int32_t use_real_tax,
+                               double real_tax_rate, double* out_host);
+int mcr_helper_rebalance(mcr_ctx* ctx, double bal1, double cb1, double bal2, double cb2,
+                         double out4_host[4]);
+
+/* ---- the batched search kernel --------------------------------------------------------- */
+
+/* Evaluates n_candidates values of working_months in ONE launch on the same Philox streams
+ * (common random numbers), replacing one sequential run_monte_carlo_simulations per probe of
+ * find_minimum_working_months (backend/simulation.py:1180-1222). success_counts_dev[c] and
+ * executed_months_dev[c] (may be NULL) are ACCUMULATED (+=), so shards can share a buffer;
+ * zero them first. */
+int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_host,
+                     int32_t n_candidates, int64_t first_path, int64_t n_paths, uint32_t flags,
+                     int64_t* success_counts_dev, uint64_t* executed_months_dev, void* stream);
+
+/* ---- device aggregations (a14/a16/a19 of SURVEY §8) ------------------------------------ */
+
+#define MCR_SEL_SKIP_NAN 0x1u /* pandas NaN-skipping quantile (WR bands, :1106-1110) */
+#define MCR_SEL_MASKED 0x2u   /* only elements with mask[i] != 0 take part            */
+
+/* Exact order-statistic quantiles with numpy 'linear' interpolation for `rows` rows of
+ * `n` doubles each (values_dev + r * ld), replacing DataFrame.quantile(q, axis=1) at
+ * backend/simulation.py:1059-1061,1091-1093,1108-1110 and Series.median/quantile at
+ * backend/simulation.py:96, backend/server.py:449-455. out_dev[r * n_q + k] is the k-th
+ * quantile of row r (NaN when the row has no valid element); counts_dev[r] (may be NULL) the
+ * number of valid elements. q_host holds fractions in [0,1]. mask_dev (MCR_SEL_MASKED) is
+ * shared by all rows. */
+int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld, int32_t rows,
+                  const uint8_t* mask_dev, const double* q_host, int32_t n_q, uint32_t sel_flags,
+                  double* out_dev, int64_t* counts_dev, void* stream);
+
+/* rates[i] = first_year_real[i] / start[i] * 100 where start[i] > 1e-6 else NaN
+ * (median_first_year_withdrawal_rate, backend/simulation.py:78-96). */
+int mcr_first_year_rates(mcr_ctx* ctx, const double* start_dev, const double* first_year_real_dev,
+                         int64_t n, double* rates_dev, void* stream);
+
+/* Equal-width histogram of values over the cohort mask (all when NULL): first min/max of the
+ * cohort, then n_bins bins with the last bin closed — numpy.histogram semantics used by
+ * backend/plotting.py:46-59 (100 bins) and frontend HistogramChart.jsx:13-60 (60 bins).
+ * minmax_dev[2] receives min,max (NaN,NaN when the cohort is empty); scale multiplies values
+ * first (plotting.py uses 1e-6, i.e. $M). hist_dev[n_bins] is ACCUMULATED. If
+ * fixed_range_host != NULL the range is taken from it (multi-GPU: range agreed first). */
+int mcr_histogram(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, int64_t n,
+                  double scale, int32_t n_bins, const double* fixed_range_host, double* minmax_dev,
+                  int64_t* hist_dev, void* stream);
+
+/* min/max of the cohort only (step 1 of the multi-GPU histogram). */
+int mcr_minmax(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, int64_t n,
+               double scale, double* minmax_dev, void* stream);
+
+/* Gather `n_cols` columns (path indices cols_host) of a time-major series into
+ * out_dev[k * rows + t] — the 5 sample paths of backend/simulation.py:1063-1078. */
+int mcr_gather_columns(mcr_ctx* ctx, const double* series_dev, int64_t ld, int32_t rows,
+                       const int64_t* cols_host, int32_t n_cols, double* out_dev, void* stream);
+
+/* ---- measurement ----------------------------------------------------------------------- */
+
+/* DFMA-chain microbenchmark: FP64-pipe issue slots per second on this device (the roofline
+ * denominator of SURVEY §8d). Synchronises. */
+int mcr_fp64_peak_slots_per_s(mcr_ctx* ctx, double* slots_per_s_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCR_H_ */
