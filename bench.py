@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — path-months/s of the Monte Carlo path engine on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3           # this repo's CUDA engine
+    python bench.py --impl reference --steps 2 --warmup 1     # the CPU arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[2] / SURVEY §8d config #3 — synthetic
+1,000,000 paths x 720 months (working_months=240, 40 retirement years), config.json values,
+equity-inflation correlation -0.5, realized-gains tax on both assets, rebalancing on, 2 income
+streams; PER GPU (weak scaling: rank r owns global paths [r*1e6, (r+1)*1e6) of one Philox
+stream). One "step" = the whole hot path for one batch: the fused timeline kernel (native
+Philox draws, fp64, yearly nominal/real/withdrawal-rate series written to HBM) + every device
+aggregation the callers need (success count, median first-year withdrawal rate, medians,
+final-balance quantiles and histograms, 7-quantile nominal/real bands, 5-quantile WR bands).
+
+`value`   = nominal path-months (N * 720 * n_gpus) / device-timed step, nothing leaves HBM.
+`e2e`     = the same metric through the reference-facing call
+            RetirementMonteCarloSimulator.run_monte_carlo_simulations(240, 1_000_000) returning
+            the reference's 7-tuple on the HOST (summary_df + band frames), wall-clocked.
+`roofline`= FP64-pipe issue slots: SURVEY §8d's W = 220 slots per executed path-month x executed
+            path-months of one launch / CUDA-event duration of the timeline kernel, against the
+            DFMA-chain peak measured in this run (the path is FP64-pipe bound, not HBM- or
+            tensor-bound; the HBM side is reported next to it).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W_SLOTS_PER_PATH_MONTH = 220.0  # 108 simple + 8.33 div*8 + 3 exp*15
+PATHS_PER_GPU = 1_000_000
+WORKING_MONTHS = 240
+METRIC = "path_months_per_sec"
+UNIT = "path-months/s"
+WORKLOAD = ("synthetic C3: 1e6 paths/GPU x 720 months (wm=240, R=40y), rho=-0.5, realized-gains tax on both "
+            "assets, rebalancing, 2 income streams; fp64; native Philox")
+
+
+def _scenario():
+    import scenarios
+
+    return dict(scenarios.SYNTH_C3)
+
+
+def _silence_logs():
+    try:
+        from loguru import logger
+
+        logger.remove()
+    except Exception:
+        pass
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (C restatement of the reference algorithm + the reference's own numpy
+# draws) on all host threads. /root/reference is pure Python and cannot travel to the GPU box,
+# so this is kind="port"; the Python reference itself measured 1.09e5 path-months/s/core in the
+# build container.
+# -------------------------------------------------------------------------------------------------
+_WORKER = {}
+
+
+def _cpu_worker_init(cfg):
+    from oracle import oracle as orc
+
+    _WORKER["p"] = orc.params_from_config(cfg)
+    _WORKER["orc"] = orc
+
+
+def _cpu_worker(part):
+    orc, p = _WORKER["orc"], _WORKER["p"]
+    shocks = orc.shocks_for_seeds(p, WORKING_MONTHS, part)  # default_rng(seed).standard_normal((n,3)) per path
+    recs, traj, real, wr = orc.run_batch(p, WORKING_MONTHS, shocks, 1, want_series=True)
+    return int(recs["success"].sum())
+
+
+def cpu_port_throughput(n_paths: int, procs: int):
+    """Reference algorithm on the host cores: SeedSequence path seeds (parent, as in the
+    reference), then one process per core drawing the numpy shocks and stepping the C port of
+    the path engine over its share of the paths (the reference fans out with
+    multiprocessing.Pool the same way, simulation.py:996-1001)."""
+    import multiprocessing as mp
+
+    from oracle import oracle as orc
+
+    cfg = _scenario()
+    orc.build()
+    sim = orc.OracleSimulator(cfg, n_threads=1)
+    sim.use_final_seeds()
+    n_rows = WORKING_MONTHS + 12 * cfg["retirement_years"]
+    pool = mp.get_context("fork").Pool(procs, initializer=_cpu_worker_init, initargs=(cfg,))
+    try:
+        pool.map(_cpu_worker, [[1, 2]] * procs)  # workers up (library loaded) before the clock starts
+        t0 = time.perf_counter()
+        seeds = sim.seeds.path_seeds(n_paths)
+        chunk = max(32, n_paths // (procs * 8))
+        ok = sum(pool.map(_cpu_worker, [seeds[i:i + chunk] for i in range(0, n_paths, chunk)]))
+        dt = time.perf_counter() - t0
+    finally:
+        pool.terminate()
+    return n_paths * n_rows / dt, dt, ok / n_paths
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = 100_000
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, _ = cpu_port_throughput(sample, threads)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = statistics.mean(v for v, _ in vals)
+    ms = statistics.mean(dt for _, dt in vals) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample} paths x 720 months per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} paths x 720 months per step (numpy PCG64 draws + C path engine, "
+                                   f"{threads} processes)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "C port of backend/simulation.py (oracle/path_oracle.c) + the reference's numpy draws; the "
+                "unmodified CPython reference measured 1.09e5 path-months/s/core in the build container",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+# the CUDA arm
+# -------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from monte_carlo_retirement_b200 import native
+    from monte_carlo_retirement_b200.config import Config
+    from monte_carlo_retirement_b200.simulation import RetirementMonteCarloSimulator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_line = None
+    if world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised in this process (the CPU arm forks workers)
+        threads = os.cpu_count() or 1
+        sample = 100_000
+        v, dt, p_ok = cpu_port_throughput(sample, threads)
+        cpu_line = {
+            "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample} paths x 720 months of the same workload in {dt:.1f} s wall (numpy SeedSequence/PCG64 "
+                      f"draws + C port of the path engine, {threads} processes); the unmodified CPython reference "
+                      "measured 1.09e5 path-months/s/core in the build container (BASELINE.md)",
+            "success_probability": p_ok * 100.0}
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    native.load_library()
+
+    cfg = Config(**_scenario())
+    sim = RetirementMonteCarloSimulator(cfg, device=local_rank)
+    sim.use_final_seeds()
+    n = PATHS_PER_GPU
+    first_path = rank * n
+    R = cfg.retirement_years
+    months = WORKING_MONTHS + 12 * R
+    ctx = sim.native_context
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(events=None):
+        agg = sim.aggregates_device(WORKING_MONTHS, n, bands=True, first_path=first_path, timeline_events=events)
+        if world > 1:
+            # the path shards need no data exchange; the tiny counters / histograms are summed over NVLink
+            dist.all_reduce(agg.batch.counters)
+            dist.all_reduce(agg.hists)
+        return agg
+
+    fp64_peak = ctx.fp64_peak_slots_per_s()
+    for _ in range(max(args.warmup, 3)):
+        agg = step()
+    barrier()
+
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        agg = step(k_events[i])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in k_events)
+    host = agg.to_host()
+    executed = host["executed_path_months"] / world if world > 1 else host["executed_path_months"]
+
+    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = n * months * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the reference-facing API, host 7-tuple (rank-local shard) ----------
+    e2e_steps = max(2, min(args.steps, 5))
+    sim.run_monte_carlo_simulations(WORKING_MONTHS, n)  # warm: pinned buffers, sample columns
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tup = sim.run_monte_carlo_simulations(WORKING_MONTHS, n)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = n * months * world / float(e2e_t[0])
+    h2d = 1024  # scenario constants + launch arguments (kernel parameter blocks); there is no bulk input
+    d2h = int(sim.last_d2h_bytes)
+
+    if rank == 0:
+        T = sim._trajectory_len(WORKING_MONTHS)
+        alg_bytes = n * ((2 * T + R) * 8 + 5 * 8 + 1 + 4)  # series + summary columns written per launch
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = executed * W_SLOTS_PER_PATH_MONTH / (kernel_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "paths_per_gpu": n, "months": months,
+                       "l2": "no HBM inputs (counter-based Philox); each step writes 1.36 GB of outputs, > 126 MB L2",
+                       "success_probability": host["success_probability"]},
+            "roofline": {
+                "bound": "fp64_pipe", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "Tslot/s",
+                "frac": achieved / fp64_peak, "traffic": None,
+                "kernel": "k_timeline<fast,philox>", "kernel_ms": kernel_ms,
+                "kernel_share_of_step": kernel_ms / ms_per_step,
+                "algorithmic_slots_per_path_month": W_SLOTS_PER_PATH_MONTH,
+                "executed_path_months_per_launch": executed,
+                "peak_source": "DFMA-chain microbenchmark measured in this run (burst, mcr_fp64_peak_slots_per_s)",
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
+                        "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(e2e_t[0]) * 1e3,
+                    "api": "RetirementMonteCarloSimulator.run_monte_carlo_simulations(240, 1_000_000) -> host 7-tuple"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    _silence_logs()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -171,9 +171,12 @@ int mcr_simulate(mcr_ctx* ctx, int seed_stream, int32_t working_months, int64_t 
 /* Replay batch: same kernel body fed with precomputed correlated shocks (the reference's own
  * numpy draws, backend/simulation.py:452-466), device layout shocks_dev[(m*3 + c) * shocks_ld
  * + i], m in [0, n_months), c in {equity, inflation, premium}. n_months must be
- * >= max(working_months + 12R, 1). Always strict arithmetic. */
+ * >= max(working_months + 12R, 1). Pass MCR_FLAG_STRICT for the parity contract (the Python
+ * mirror always does); flags == 0 runs the fast arithmetic on the same inputs, which is how the
+ * tests bound the fast-vs-strict drift. */
 int mcr_replay(mcr_ctx* ctx, const double* shocks_dev, int64_t shocks_ld, int32_t n_months,
-               int32_t working_months, int64_t n_paths, const mcr_outputs* out, void* stream);
+               int32_t working_months, int64_t n_paths, uint32_t flags, const mcr_outputs* out,
+               void* stream);
 
 /* One path from HOST shocks[n_months][3] (row-major, as `_draw_shock_path` returns) to HOST
  * outputs: replaces a direct call of `_run_single_simulation_path`
@@ -193,6 +196,14 @@ int mcr_helper_net_liquidation(mcr_ctx* ctx, double bal, double cost_basis, int3
 int mcr_helper_rebalance(mcr_ctx* ctx, double bal1, double cb1, double bal2, double cb2,
                          double out4_host[4]);
 
+/* Native shocks in the replay layout: shocks_dev[(m*3 + c) * shocks_ld + i] for global paths
+ * first_path + i — the device analogue of `_draw_shock_path` (backend/simulation.py:452-466).
+ * Feeding them to mcr_replay (or to the CPU oracle) reproduces mcr_simulate with
+ * MCR_FLAG_STRICT path for path. */
+int mcr_draw_shocks(mcr_ctx* ctx, int seed_stream, int64_t first_path, int64_t n_paths,
+                    int32_t n_months, uint32_t flags, double* shocks_dev, int64_t shocks_ld,
+                    void* stream);
+
 /* ---- the batched search kernel --------------------------------------------------------- */
 
 /* Evaluates n_candidates values of working_months in ONE launch on the same Philox streams
@@ -206,16 +217,19 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
 
 /* ---- device aggregations (a14/a16/a19 of SURVEY §8) ------------------------------------ */
 
-#define MCR_SEL_SKIP_NAN 0x1u /* pandas NaN-skipping quantile (WR bands, :1106-1110) */
-#define MCR_SEL_MASKED 0x2u   /* only elements with mask[i] != 0 take part            */
+#define MCR_SEL_MEDIAN 0x1u /* np.median rule: mean of the two middle order statistics
+                               (Series.median at simulation.py:96, server.py:449-450);
+                               q_host is ignored and n_q results per row are all the median */
 
-/* Exact order-statistic quantiles with numpy 'linear' interpolation for `rows` rows of
- * `n` doubles each (values_dev + r * ld), replacing DataFrame.quantile(q, axis=1) at
- * backend/simulation.py:1059-1061,1091-1093,1108-1110 and Series.median/quantile at
- * backend/simulation.py:96, backend/server.py:449-455. out_dev[r * n_q + k] is the k-th
- * quantile of row r (NaN when the row has no valid element); counts_dev[r] (may be NULL) the
- * number of valid elements. q_host holds fractions in [0,1]. mask_dev (MCR_SEL_MASKED) is
- * shared by all rows. */
+/* Exact order-statistic quantiles of `rows` rows of `n` doubles each (values_dev + r * ld) with
+ * numpy's 'linear' interpolation, replacing DataFrame.quantile(q, axis=1) at
+ * backend/simulation.py:1059-1061,1091-1093,1108-1110 and Series.quantile/median at
+ * backend/simulation.py:96, backend/server.py:449-455. NaN elements never take part (pandas
+ * skips them: the WR bands of :1106-1110); when mask_dev != NULL only elements with
+ * mask_dev[i] != 0 take part (one mask shared by all rows: the successful-path cohort).
+ * out_dev[r * n_q + k] is the k-th quantile of row r (NaN when the row has no valid element);
+ * counts_dev[r] (may be NULL) receives the number of valid elements (the WR observation
+ * counts of :1111-1113). q_host holds n_q <= 16 fractions in [0,1]. */
 int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld, int32_t rows,
                   const uint8_t* mask_dev, const double* q_host, int32_t n_q, uint32_t sel_flags,
                   double* out_dev, int64_t* counts_dev, void* stream);
@@ -225,19 +239,21 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
 int mcr_first_year_rates(mcr_ctx* ctx, const double* start_dev, const double* first_year_real_dev,
                          int64_t n, double* rates_dev, void* stream);
 
-/* Equal-width histogram of values over the cohort mask (all when NULL): first min/max of the
- * cohort, then n_bins bins with the last bin closed — numpy.histogram semantics used by
- * backend/plotting.py:46-59 (100 bins) and frontend HistogramChart.jsx:13-60 (60 bins).
- * minmax_dev[2] receives min,max (NaN,NaN when the cohort is empty); scale multiplies values
- * first (plotting.py uses 1e-6, i.e. $M). hist_dev[n_bins] is ACCUMULATED. If
- * fixed_range_host != NULL the range is taken from it (multi-GPU: range agreed first). */
-int mcr_histogram(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, int64_t n,
-                  double scale, int32_t n_bins, const double* fixed_range_host, double* minmax_dev,
-                  int64_t* hist_dev, void* stream);
+#define MCR_HIST_NUMPY 0 /* numpy.histogram / matplotlib plt.hist(bins=n) — plotting.py:46-59  */
+#define MCR_HIST_FLOOR 1 /* idx = min(floor((v-min)/width), n-1) — HistogramChart.jsx:13-60   */
 
-/* min/max of the cohort only (step 1 of the multi-GPU histogram). */
+/* min/max of (values / divisor) over the cohort mask (all when NULL) into minmax_dev[2]
+ * (NaN, NaN when the cohort is empty). */
 int mcr_minmax(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, int64_t n,
-               double scale, double* minmax_dev, void* stream);
+               double divisor, double* minmax_dev, void* stream);
+
+/* Equal-width histogram of (values / divisor) over the cohort: n_bins bins over
+ * range_dev[0..1] (from mcr_minmax, or agreed across GPUs first). plotting.py divides by 1e6
+ * ($M) and uses 100 bins with numpy semantics; the dashboard uses 60 bins with floor binning.
+ * hist_dev[n_bins] is ACCUMULATED (+=). */
+int mcr_histogram(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, int64_t n,
+                  double divisor, int32_t n_bins, int32_t mode, const double* range_dev,
+                  int64_t* hist_dev, void* stream);
 
 /* Gather `n_cols` columns (path indices cols_host) of a time-major series into
  * out_dev[k * rows + t] — the 5 sample paths of backend/simulation.py:1063-1078. */
@@ -246,9 +262,12 @@ int mcr_gather_columns(mcr_ctx* ctx, const double* series_dev, int64_t ld, int32
 
 /* ---- measurement ----------------------------------------------------------------------- */
 
-/* DFMA-chain microbenchmark: FP64-pipe issue slots per second on this device (the roofline
- * denominator of SURVEY §8d). Synchronises. */
+/* DFMA-chain microbenchmark: FP64-pipe issue slots (lane-instructions) per second on this
+ * device — the roofline denominator of SURVEY §8d. Synchronises. */
 int mcr_fp64_peak_slots_per_s(mcr_ctx* ctx, double* slots_per_s_host);
+
+/* Kernels launched by this context so far (the `gpu_launches` claim of bench.py). */
+int64_t mcr_launch_count(const mcr_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,46 @@
+// mcr_internal.h — host/device shared argument blocks and the launcher tables that the two
+// arithmetic builds (strict / fast) export to the C-ABI layer (mcr_api.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mcr.h"
+
+namespace mcr {
+
+struct DevParams;
+
+struct TimelineArgs {
+  int32_t wm;
+  uint32_t k0, k1, seed_stream;   // Philox key words + seed stream (counter word 3)
+  int64_t first_path, n_paths;
+  int32_t start_month[MCR_MAX_STREAMS];  // stream_payment_start_month_index per stream
+  const double* shocks;           // replay only
+  int64_t shocks_ld;
+  mcr_outputs out;
+};
+
+struct SearchArgs {
+  uint32_t k0, k1, seed_stream;
+  int32_t n_candidates;
+  int64_t first_path, n_paths;
+  const int32_t* wm;              // [n_candidates] device, sorted longest first
+  const int32_t* slot;            // [n_candidates] device: index into the caller's arrays
+  const int32_t* start_month;     // [n_candidates][MCR_MAX_STREAMS] device
+  int64_t* success_counts;        // caller buffer, accumulated
+  uint64_t* executed_months;      // caller buffer or NULL, accumulated
+};
+
+struct Launchers {
+  cudaError_t (*timeline)(const DevParams&, const TimelineArgs&, bool replay, cudaStream_t);
+  cudaError_t (*search)(const DevParams&, const SearchArgs&, cudaStream_t);
+  cudaError_t (*draw)(const DevParams&, uint32_t k0, uint32_t k1, uint32_t seed_stream, int64_t first_path,
+                      int64_t n_paths, int32_t n_months, double* shocks, int64_t ld, cudaStream_t);
+  cudaError_t (*helper)(const DevParams&, int which, double a, double b, double c, double d, int use_tax,
+                        double rate, double* out, cudaStream_t);
+};
+
+const Launchers& strict_launchers();
+const Launchers& fast_launchers();
+
+}  // namespace mcr

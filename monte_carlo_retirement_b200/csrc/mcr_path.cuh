@@ -1,0 +1,448 @@
+// mcr_path.cuh — the per-path timeline state machine, one thread = one path, all state in
+// registers. Behavioural spec: /root/reference/backend/simulation.py:476-950
+// (_run_single_simulation_path) with its helpers :201-450; the step order is the reference's
+// (SURVEY Appendix A). This header is compiled twice:
+//   * mcr_kernels_strict.cu  (-fmad=false): every product/sum rounds separately, in the
+//     reference's operation order — the parity build used by replay / single-path / helpers;
+//   * mcr_kernels_fast.cu    (-fmad=true): same formulas, FMA contraction, shared reciprocals
+//     and a short-range exp — the throughput build used by native-RNG runs.
+// Bit-exact elisions used in BOTH builds: an asset whose realized-gains tax
+// is inactive (flag off or rate 0) has effective tax fraction 0, so `target / max(eps, 1.0)`
+// == target, its sale pays no tax and its cost basis never reaches an output.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/mcr.h"
+
+namespace mcr {
+
+constexpr double kEps = MCR_SMALL_EPSILON;
+constexpr int kMPY = MCR_MONTHS_PER_YEAR;
+
+struct DevStream {
+  double amount;        // monthly_amount_today
+  double net_factor;    // 1.0 - tax_rate
+  int32_t duration;     // months, -1 == None
+  int32_t indexed;
+};
+
+// Scenario constants, passed by value as a __grid_constant__ kernel parameter (uniform loads
+// from the constant bank). Everything here is derived on the host by mcr_create.
+struct DevParams {
+  double B0, C0, growth1p, E, a1, a2;
+  double mu1, sg1, muI, sgI, muP, sgP;  // monthly: mu_log/12, sigma_log/sqrt(12)
+  double rho, rho_c;                    // equity-inflation correlation, sqrt(max(0,1-rho^2))
+  double rate1, rate2;                  // realized-gains tax rates
+  double ann1, ann2;                    // annual mark-to-market rates
+  float rho_f, rho_c_f;
+  int32_t use1, use2;      // inv{1,2}_use_realized_gains_tax_system
+  int32_t taxed1, taxed2;  // use && rate > 0 : realized tax actually bites
+  int32_t growth_on;       // contribution_growth_rate_annual > 0
+  int32_t annual_any;      // some asset can owe annual tax (needs the P&L accumulators)
+  int32_t R;               // retirement_years
+  int32_t n_streams;
+  DevStream streams[MCR_MAX_STREAMS];
+};
+
+struct PathOut {
+  double start_balance, final_balance, fy_gross, fy_real, infl_ret;
+  int32_t success;
+  int32_t ruin_month;  // -1 == NaN
+  uint32_t executed;   // months stepped (shock rows consumed)
+};
+
+// CPython max(a, b) / min(a, b): first argument wins ties and NaN compares.
+__device__ __forceinline__ double pmax(double a, double b) { return (b > a) ? b : a; }
+__device__ __forceinline__ double pmin(double a, double b) { return (b < a) ? b : a; }
+
+// ---------------------------------------------------------------------------------------------
+// math policy
+// ---------------------------------------------------------------------------------------------
+template <bool FAST>
+struct Math {
+  // reciprocal to ~1 ulp: MUFU.RCP64H seed + the 5-DFMA refinement (fast build only)
+  static __device__ __forceinline__ double rcp(double b) {
+    if constexpr (FAST) {
+      double x0;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(b));
+      double e = fma(-b, x0, 1.0);
+      double e2 = fma(e, e, e);
+      double x1 = fma(x0, e2, x0);
+      double e3 = fma(-b, x1, 1.0);
+      return fma(x1, e3, x1);
+    } else {
+      return 1.0 / b;
+    }
+  }
+  // monthly gross factor exp(mu + sg * z) — simulation.py:468-474
+  static __device__ __forceinline__ double gross(double mu, double sg, double z) {
+    const double x = mu + sg * z;  // strict: two roundings (no FMA); fast: one DFMA
+    if constexpr (FAST) {
+      // |x| is a monthly log-return, far inside [-0.5 ln2, 0.5 ln2] for any sane scenario: a
+      // degree-13 Taylor polynomial on the unreduced argument (truncation < 3e-18 relative at
+      // |x| = 0.34, 13 DFMA instead of the library's 17 FP64 ops + range reduction), with the
+      // general routine as the (warp-rare) fallback.
+      if (fabs(x) < 0.34) {
+        double p = 1.6059043836821613e-10;              // 1/13!
+        p = fma(p, x, 2.08767569878681e-09);            // 1/12!
+        p = fma(p, x, 2.505210838544172e-08);           // 1/11!
+        p = fma(p, x, 2.755731922398589e-07);           // 1/10!
+        p = fma(p, x, 2.7557319223985893e-06);           // 1/9!
+        p = fma(p, x, 2.48015873015873e-05);            // 1/8!
+        p = fma(p, x, 1.984126984126984e-04);           // 1/7!
+        p = fma(p, x, 1.388888888888889e-03);           // 1/6!
+        p = fma(p, x, 8.333333333333333e-03);           // 1/5!
+        p = fma(p, x, 4.1666666666666664e-02);           // 1/4!
+        p = fma(p, x, 1.6666666666666666e-01);           // 1/3!
+        p = fma(p, x, 0.5);
+        p = fma(p, x, 1.0);
+        return fma(p, x, 1.0);
+      }
+      return exp(x);
+    } else {
+      return exp(x);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// helpers — simulation.py:201-450. FULL = also maintain the cost basis of an untaxed asset
+// (needed only by the helper entry points that RETURN the basis).
+// ---------------------------------------------------------------------------------------------
+
+// _net_liquidation_value — simulation.py:256-272
+__device__ __forceinline__ double net_liq(double bal, double cb, bool taxed, double rate) {
+  if (bal <= kEps) return 0.0;
+  if (!taxed) return pmax(0.0, bal);  // tax == 0.0, bal - 0.0 == bal
+  const double gain = pmax(0.0, bal - cb);
+  return pmax(0.0, bal - gain * rate);
+}
+
+// _calculate_withdrawal_and_update — simulation.py:201-254
+template <bool FAST, bool FULL>
+__device__ __forceinline__ void withdraw(double& bal, double& cb, double target, bool taxed, double rate,
+                                         double& gross, double& net) {
+  if (bal <= kEps || target <= 0) {  // :218-219
+    bal = pmax(0.0, bal);
+    cb = pmax(0.0, cb);
+    gross = 0.0;
+    net = 0.0;
+    return;
+  }
+  if (!taxed && !FULL) {
+    // effective tax fraction 0 -> net_fraction == 1.0, target / 1.0 == target, tax_paid == 0.
+    gross = pmin(target, bal);
+    net = pmax(0.0, gross);
+    double nb = pmax(0.0, bal - gross);
+    if (nb <= kEps) nb = 0.0;
+    bal = nb;
+    return;  // cost basis of an untaxed asset is dead state
+  }
+  double gf, fs;
+  if constexpr (FAST) {
+    const double rb = Math<FAST>::rcp(bal);
+    gf = pmax(0.0, bal - cb) * rb;
+    const double etf = taxed ? gf * rate : 0.0;
+    const double nf = pmax(kEps, 1.0 - etf);
+    gross = pmin(target * Math<FAST>::rcp(nf), bal);
+    fs = pmin(1.0, gross * rb);
+  } else {
+    gf = pmax(0.0, bal - cb) / bal;                      // :221
+    const double etf = taxed ? gf * rate : 0.0;          // :222-226
+    const double nf = pmax(kEps, 1.0 - etf);             // :227
+    gross = pmin(target / nf, bal);                      // :228-231
+    fs = pmin(1.0, gross / bal);                         // :233
+  }
+  const double br = pmin(cb, cb * fs);                   // :234
+  const double tg = pmax(0.0, gross - br);               // :235
+  const double tax = taxed ? tg * rate : 0.0;            // :236-240
+  net = pmax(0.0, gross - tax);                          // :241
+  double nb = pmax(0.0, bal - gross);                    // :243
+  double ncb = pmax(0.0, cb - br);                       // :244
+  if (nb <= kEps) { nb = 0.0; ncb = 0.0; }               // :245-247
+  bal = nb;
+  cb = ncb;
+}
+
+// _rebalance_portfolio — simulation.py:274-359. The sell-asset-1 / sell-asset-2 branches are
+// folded into one straight-line body by selecting the roles (the direction differs per lane,
+// the flags do not), so a warp never executes both.
+template <bool FAST, bool FULL>
+__device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
+  const double total = b1 + b2;
+  if (total <= kEps) return;                              // :290-291
+  const double drift1 = b1 - total * P.a1;                // :293-294
+  if (fabs(drift1) <= kEps) return;                       // :295-296
+  const bool sell1 = drift1 > 0;
+  const double drift2 = b2 - total * P.a2;                // :328 (recomputed, not -drift1)
+  const double bs = sell1 ? b1 : b2;
+  const double cbs = sell1 ? cb1 : cb2;
+  const double bo = sell1 ? b2 : b1;
+  const double cbo = sell1 ? cb2 : cb1;
+  const double drift = sell1 ? drift1 : drift2;
+  double sale, br = 0.0, buy;
+  // the rebalance consults only the `use` flag (:302-306); use && rate == 0 gives tpd == 0.0
+  // exactly, so `taxed` decides the arithmetic in both cases.
+  const bool both_plain = !P.taxed1 && !P.taxed2 && !FULL;
+  if (both_plain) {
+    sale = pmin(bs, drift);          // denominator == max(eps, 1.0 - a*0.0) == 1.0
+    buy = sale;                      // tax_paid == 0.0
+  } else {
+    const double rate = sell1 ? (P.use1 ? P.rate1 : 0.0) : (P.use2 ? P.rate2 : 0.0);
+    const double as = sell1 ? P.a1 : P.a2;
+    double fs;
+    if constexpr (FAST) {
+      const double rb = Math<FAST>::rcp(bs);
+      const double gf = pmax(0.0, bs - cbs) * rb;
+      const double den = pmax(kEps, 1.0 - as * (gf * rate));
+      sale = pmin(bs, drift * Math<FAST>::rcp(den));
+      fs = sale * rb;
+    } else {
+      const double gf = pmax(0.0, bs - cbs) / bs;           // :301 / :329
+      const double den = pmax(kEps, 1.0 - as * (gf * rate)); // :302-310
+      sale = pmin(bs, drift / den);                         // :311
+      fs = sale / bs;                                       // :312
+    }
+    br = pmin(cbs, cbs * fs);                               // :313
+    const double tg = pmax(0.0, sale - br);                 // :314
+    buy = sale - tg * rate;                                 // :315-320
+  }
+  double nbs = pmax(0.0, bs - sale);                        // :322
+  double ncbs = pmax(0.0, cbs - br);                        // :323
+  double nbo = bo + buy;                                    // :324
+  double ncbo = cbo + buy;                                  // :325
+  if (nbs <= kEps) { nbs = 0.0; ncbs = 0.0; }               // :355-358
+  if (nbo <= kEps) { nbo = 0.0; ncbo = 0.0; }
+  b1 = sell1 ? nbs : nbo;
+  cb1 = sell1 ? ncbs : ncbo;
+  b2 = sell1 ? nbo : nbs;
+  cb2 = sell1 ? ncbo : ncbs;
+}
+
+// _apply_annual_gain_taxes — simulation.py:361-450. Returns tax_failed.
+template <bool FAST, bool FULL>
+__device__ __forceinline__ bool annual_tax(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2,
+                                           double g1, double g2) {
+  const double due1 = !P.use1 ? pmax(0.0, g1) * P.ann1 : 0.0;   // :380-384
+  const double due2 = !P.use2 ? pmax(0.0, g2) * P.ann2 : 0.0;   // :385-389
+  const double due = due1 + due2;
+  const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);      // :392-403
+  const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
+  const double cap = cap1 + cap2;
+  const double pay = pmin(due, cap);                            // :405
+  bool failed = pay < due - kEps;                               // :406
+  if (cap > kEps && pay > 0) {                                  // :408-430
+    const double share1 = cap1 / cap;
+    const double share2 = 1.0 - share1;
+    double gw, n1, n2;
+    withdraw<FAST, FULL>(b1, cb1, pay * share1, P.taxed1, P.rate1, gw, n1);
+    withdraw<FAST, FULL>(b2, cb2, pay * share2, P.taxed2, P.rate2, gw, n2);
+    if (n1 + n2 < due - kEps) failed = true;
+  }
+  rebalance<FAST, FULL>(P, b1, cb1, b2, cb2);                   // :432-442
+  return failed;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sinks for the yearly series
+// ---------------------------------------------------------------------------------------------
+struct NullSink {
+  static constexpr bool kActive = false;
+  __device__ __forceinline__ void point(int, double, double) {}
+  __device__ __forceinline__ void wr(int, double) {}
+};
+
+// time-major [t][ld]: a warp's 32 paths store 256 contiguous bytes per point
+struct SeriesSink {
+  static constexpr bool kActive = true;
+  double* traj;  // may be NULL
+  double* real;  // may be NULL
+  double* wrp;   // may be NULL
+  int64_t ld;
+  __device__ __forceinline__ void point(int t, double nominal, double price) {
+    if (traj) __stcs(traj + (int64_t)t * ld, nominal);
+    if (real) __stcs(real + (int64_t)t * ld, price > kEps ? nominal / price : 0.0);  // :928-931
+  }
+  __device__ __forceinline__ void wr(int y, double v) {
+    if (wrp) __stcs(wrp + (int64_t)y * ld, v);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the timeline
+// ---------------------------------------------------------------------------------------------
+template <bool FAST, class Shock, class Sink>
+__device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
+                                             const int32_t* __restrict__ start_month, Shock& shock,
+                                             Sink& sink, PathOut& o, int& years_observed) {
+  const int R = P.R;
+  double b1 = P.B0 * P.a1;                                   // :499-502
+  double b2 = P.B0 - b1;
+  double cb1 = b1, cb2 = b2;
+  double contrib = P.C0;
+  double g1 = 0.0, g2 = 0.0;
+  double level = 1.0;
+  bool pre_fail = false;
+  uint32_t executed = 0;
+  int t = 0;
+  sink.point(t++, P.B0, 1.0);                                // :490-492
+
+  // ---- accumulation — :513-579
+  int moy = 0;  // (m-1) % 12
+  for (int m = 1; m <= wm; ++m) {
+    if (moy == 0 && m > 1 && P.growth_on) contrib *= P.growth1p;   // :514-517
+    double ze, zi, zp;
+    shock.next(ze, zi, zp);
+    ++executed;
+    const double G1 = Math<FAST>::gross(P.mu1, P.sg1, ze);
+    const double GI = Math<FAST>::gross(P.muI, P.sgI, zi);
+    const double GP = Math<FAST>::gross(P.muP, P.sgP, zp);
+    const double G2 = GI * GP;                                     // :532
+    if (P.annual_any) {
+      g1 += b1 * (G1 - 1.0);                                       // :534-535
+      g2 += b2 * (G2 - 1.0);
+    }
+    b1 *= G1;
+    b2 *= G2;
+    level *= GI;
+    const double k1 = contrib * P.a1;                              // :540-547
+    const double k2 = contrib - k1;
+    b1 += k1; cb1 += k1;
+    b2 += k2; cb2 += k2;
+    rebalance<FAST, false>(P, b1, cb1, b2, cb2);                   // :549-553
+    if (++moy == kMPY) {                                           // m % 12 == 0 — :557-579
+      moy = 0;
+      if (annual_tax<FAST, false>(P, b1, cb1, b2, cb2, g1, g2)) pre_fail = true;
+      sink.point(t++, b1 + b2, level);
+      g1 = 0.0; g2 = 0.0;
+    }
+  }
+
+  const double S0 = b1 + b2;                                       // :581-582
+  const double level_ret = level;
+  if (wm > 0 && moy != 0) sink.point(t++, S0, level_ret);          // :590-594
+
+  double locked[MCR_MAX_STREAMS];
+  uint32_t locked_mask = 0;
+  double fy_gross = 0.0, fy_real = 0.0;
+  bool ok = !pre_fail;                                             // :627-629
+  int ruin = pre_fail ? 0 : -1;
+  int tax_moy = moy;  // (absolute month) % 12 of the last completed month
+  int y = 0;
+  int n_obs = 0;      // retirement years with a withdrawal-rate observation
+
+  // ---- decumulation — :632-868
+  for (; y < R && !pre_fail; ++y) {
+    double yr_g1 = 0.0, yr_g2 = 0.0, yr_real = 0.0;
+    bool failed = false;
+    int r = y * kMPY;
+    for (int j = 0; j < kMPY; ++j, ++r) {
+      const double level0 = level;                                 // :644-647
+      const double need_nominal = P.E * level0;
+      double income = 0.0;
+      for (int k = 0; k < P.n_streams; ++k) {                      // :650-677
+        const int s0 = start_month[k];
+        const int dur = P.streams[k].duration;
+        const bool active = r >= s0 && (dur < 0 || r < s0 + dur);
+        if (!active) continue;
+        double nominal;
+        if (P.streams[k].indexed) {
+          nominal = P.streams[k].amount * level0;
+        } else {
+          if (!(locked_mask & (1u << k))) {
+            locked[k] = P.streams[k].amount * level0;
+            locked_mask |= 1u << k;
+          }
+          nominal = locked[k];
+        }
+        income += nominal * P.streams[k].net_factor;
+      }
+      const double need = pmax(0.0, need_nominal - income);        // :679-682
+      if (b1 + b2 <= kEps && need > kEps) { failed = true; break; }  // :684-690
+
+      double ze, zi, zp;
+      shock.next(ze, zi, zp);
+      ++executed;
+      const double G1 = Math<FAST>::gross(P.mu1, P.sg1, ze);
+      const double GI = Math<FAST>::gross(P.muI, P.sgI, zi);
+      const double GP = Math<FAST>::gross(P.muP, P.sgP, zp);
+      const double G2 = GI * GP;
+      if (P.annual_any) {
+        g1 += b1 * (G1 - 1.0);                                     // :706-711
+        g2 += b2 * (G2 - 1.0);
+      }
+      b1 *= G1;
+      b2 *= G2;
+      level *= GI;
+      if (b1 + b2 <= kEps && need > kEps) {                        // :715-724
+        b1 = pmax(0.0, b1);
+        b2 = pmax(0.0, b2);
+        failed = true;
+        break;
+      }
+      const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);     // :726-737
+      const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
+      const double cap = cap1 + cap2;
+      const double target = pmax(0.0, pmin(need, cap));            // :739-742
+      if (need > kEps && target < need - kEps) failed = true;      // :743-748
+      const double w1 = cap > kEps ? cap1 / cap : P.a1;            // :750-755
+      const double w2 = 1.0 - w1;
+      double gw1, nw1, gw2, nw2;
+      withdraw<FAST, false>(b1, cb1, target * w1, P.taxed1, P.rate1, gw1, nw1);   // :757-777
+      withdraw<FAST, false>(b2, cb2, target * w2, P.taxed2, P.rate2, gw2, nw2);
+      yr_g1 += gw1;
+      yr_g2 += gw2;
+      yr_real += (gw1 + gw2) * level_ret / pmax(level0, kEps);     // :778-782
+      if (need > kEps && nw1 + nw2 < need - kEps) failed = true;   // :784-790
+      rebalance<FAST, false>(P, b1, cb1, b2, cb2);                 // :792-796
+      if (++tax_moy == kMPY) tax_moy = 0;
+      if (!failed && tax_moy == 0) {                               // :798-822
+        const bool tf = annual_tax<FAST, false>(P, b1, cb1, b2, cb2, g1, g2);
+        g1 = 0.0; g2 = 0.0;
+        if (tf) failed = true;
+      }
+      if (failed) { ruin = r + 1; break; }                         // :824-828
+    }
+    const double yr_gross = yr_g1 + yr_g2;
+    if (failed) {                                                  // :842-857
+      ok = false;
+      if (ruin < 0) ruin = r + 1;
+      sink.point(t++, pmax(0.0, b1 + b2), level);
+      sink.wr(y, CUDART_NAN);
+      if (y == 0) { fy_gross = yr_gross; fy_real = yr_real; }
+      ++y;
+      break;
+    }
+    sink.wr(y, S0 > kEps ? (yr_real / S0) * 100.0 : 0.0);          // :834-840,859
+    n_obs = y + 1;
+    if (y == 0) { fy_gross = yr_gross; fy_real = yr_real; }
+    sink.point(t++, b1 + b2, level);
+  }
+
+  // ---- final partial tax period — :873-898
+  if (ok && tax_moy != 0) {
+    if (annual_tax<FAST, false>(P, b1, cb1, b2, cb2, g1, g2)) { ok = false; ruin = R * kMPY; }
+    sink.point(t - 1, b1 + b2, level);   // overwrites the last yearly sample
+  }
+
+  // ---- padding — :902-937 (failed paths pad 0.0; WR pads NaN)
+  if (Sink::kActive) {
+    const int T = 1 + (wm + kMPY - 1) / kMPY + R;
+    for (; t < T; ++t) sink.point(t, 0.0, 1.0);
+    for (; y < R; ++y) sink.wr(y, CUDART_NAN);
+  }
+
+  o.start_balance = S0;
+  o.final_balance = pmax(0.0, b1 + b2);
+  o.fy_gross = fy_gross;
+  o.fy_real = fy_real;
+  o.infl_ret = level_ret;
+  o.success = ok ? 1 : 0;
+  o.ruin_month = ruin;
+  o.executed = executed;
+  years_observed = n_obs;
+}
+
+}  // namespace mcr

@@ -1,0 +1,32 @@
+// mcr_reduce.h — launch interface of the device aggregations (mcr_reduce.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mcr.h"
+
+namespace mcr {
+
+constexpr int kMaxQuantiles = 16;
+
+struct QuantileSpec {
+  int32_t n_q;
+  int32_t median;  // 1: np.median rule (mean of the two middle order statistics), q ignored
+  double q[kMaxQuantiles];
+};
+
+size_t quantile_workspace_bytes(int rows);
+cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask,
+                             const QuantileSpec& spec, double* out, int64_t* counts, void* workspace, cudaStream_t st,
+                             int* n_launches);
+cudaError_t launch_rates(const double* start, const double* fy_real, int64_t n, double* rates, cudaStream_t st);
+cudaError_t launch_minmax(const double* x, const uint8_t* mask, int64_t n, double divisor, unsigned long long* keys2,
+                          double* minmax, cudaStream_t st);
+cudaError_t launch_histogram(const double* x, const uint8_t* mask, int64_t n, double divisor, int n_bins, int mode,
+                             const double* range_dev, int64_t* hist, cudaStream_t st);
+cudaError_t launch_gather(const double* series, int64_t ld, int rows, const int64_t* cols_dev, int n_cols, double* out,
+                          cudaStream_t st);
+cudaError_t launch_fp64_peak(int sm_count, int iters, double* sink, cudaStream_t st, int* total_threads,
+                             int* dfma_per_thread);
+
+}  // namespace mcr

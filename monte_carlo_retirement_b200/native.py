@@ -1,0 +1,286 @@
+"""ctypes binding of libmcr_b200.so — the thin layer between the Python mirror of the
+reference's `simulation` module and the hand-written sm_100a CUDA engine (include/mcr.h).
+
+There is NO CPU fallback: loading fails loudly when the library is missing and every compute
+call raises when no CUDA device is usable. PyTorch is used only to own device buffers and
+streams; pointers cross the ABI as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Any, Optional, Sequence
+
+MAX_STREAMS = 16
+FLAG_STRICT = 0x1
+STREAM_SEARCH = 0
+STREAM_FINAL = 1
+SEL_MEDIAN = 0x1
+HIST_NUMPY = 0
+HIST_FLOOR = 1
+E_INVAL = -1
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "_lib", "libmcr_b200.so")
+
+
+class IncomeStream(C.Structure):
+    _fields_ = [
+        ("monthly_amount_today", C.c_double),
+        ("start_at_age", C.c_double),
+        ("tax_rate", C.c_double),
+        ("duration_years", C.c_int32),
+        ("inflation_indexed", C.c_int32),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("initial_balance", C.c_double),
+        ("monthly_contribution", C.c_double),
+        ("contribution_growth_rate_annual", C.c_double),
+        ("monthly_expenses", C.c_double),
+        ("current_age", C.c_double),
+        ("allocation_inv1_pct", C.c_double),
+        ("inv1_mu_log", C.c_double),
+        ("inv1_sigma_log", C.c_double),
+        ("inf_mu_log", C.c_double),
+        ("inf_sigma_log", C.c_double),
+        ("prem_mu_log", C.c_double),
+        ("prem_sigma_log", C.c_double),
+        ("equity_inflation_rho", C.c_double),
+        ("inv1_annual_tax_on_gains_rate", C.c_double),
+        ("inv1_realized_gains_tax_rate", C.c_double),
+        ("inv2_annual_tax_on_gains_rate", C.c_double),
+        ("inv2_realized_gains_tax_rate", C.c_double),
+        ("inv1_use_realized_gains_tax_system", C.c_int32),
+        ("inv2_use_realized_gains_tax_system", C.c_int32),
+        ("retirement_years", C.c_int32),
+        ("n_streams", C.c_int32),
+        ("streams", IncomeStream * MAX_STREAMS),
+    ]
+
+
+class Outputs(C.Structure):
+    _fields_ = [
+        ("start_balance", C.c_void_p),
+        ("final_balance", C.c_void_p),
+        ("success", C.c_void_p),
+        ("ruin_month", C.c_void_p),
+        ("first_year_gross", C.c_void_p),
+        ("first_year_real", C.c_void_p),
+        ("inflation_at_ret", C.c_void_p),
+        ("trajectory", C.c_void_p),
+        ("real_trajectory", C.c_void_p),
+        ("wr_trajectory", C.c_void_p),
+        ("series_ld", C.c_int64),
+        ("success_count", C.c_void_p),
+        ("wr_obs_count", C.c_void_p),
+        ("ruin_month_hist", C.c_void_p),
+        ("executed_months", C.c_void_p),
+    ]
+
+
+class PathRecord(C.Structure):
+    _fields_ = [
+        ("start_balance", C.c_double),
+        ("final_balance", C.c_double),
+        ("first_year_gross", C.c_double),
+        ("first_year_real", C.c_double),
+        ("inflation_at_ret", C.c_double),
+        ("success", C.c_int32),
+        ("ruin_month", C.c_int32),
+        ("trajectory_len", C.c_int32),
+        ("wr_len", C.c_int32),
+    ]
+
+
+# every symbol include/mcr.h declares: (restype, argtypes)
+_VP, _I32, _I64, _U32, _U64, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+SIGNATURES = {
+    "mcr_abi_version": (C.c_int, []),
+    "mcr_create": (C.c_int, [C.POINTER(Params), _U64, C.c_int, C.POINTER(_VP)]),
+    "mcr_destroy": (C.c_int, [_VP]),
+    "mcr_last_error": (C.c_char_p, [_VP]),
+    "mcr_launch_count": (_I64, [_VP]),
+    "mcr_stream_start_month": (_I32, [_D, _I32, _D]),
+    "mcr_trajectory_len": (_I32, [_I32, _I32]),
+    "mcr_simulate": (C.c_int, [_VP, C.c_int, _I32, _I64, _I64, _U32, C.POINTER(Outputs), _VP]),
+    "mcr_replay": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _I64, _U32, C.POINTER(Outputs), _VP]),
+    "mcr_single_path": (C.c_int, [_VP, _I32, _VP, _I32, C.POINTER(PathRecord), _VP, _VP, _VP]),
+    "mcr_helper_withdraw": (C.c_int, [_VP, _D, _D, _D, _I32, _D, C.POINTER(_D)]),
+    "mcr_helper_net_liquidation": (C.c_int, [_VP, _D, _D, _I32, _D, C.POINTER(_D)]),
+    "mcr_helper_rebalance": (C.c_int, [_VP, _D, _D, _D, _D, C.POINTER(_D)]),
+    "mcr_draw_shocks": (C.c_int, [_VP, C.c_int, _I64, _I64, _I32, _U32, _VP, _I64, _VP]),
+    "mcr_search_batch": (C.c_int, [_VP, C.c_int, C.POINTER(_I32), _I32, _I64, _I64, _U32, _VP, _VP, _VP]),
+    "mcr_quantiles": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, C.POINTER(_D), _I32, _U32, _VP, _VP, _VP]),
+    "mcr_first_year_rates": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP]),
+    "mcr_minmax": (C.c_int, [_VP, _VP, _VP, _I64, _D, _VP, _VP]),
+    "mcr_histogram": (C.c_int, [_VP, _VP, _VP, _I64, _D, _I32, _I32, _VP, _VP, _VP]),
+    "mcr_gather_columns": (C.c_int, [_VP, _VP, _I64, _I32, C.POINTER(_I64), _I32, _VP, _VP]),
+    "mcr_fp64_peak_slots_per_s": (C.c_int, [_VP, C.POINTER(_D)]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """dlopen the engine and bind every exported symbol. Raises if it is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise RuntimeError(
+                f"{p} is missing: build it with `python -m monte_carlo_retirement_b200.build` "
+                "(this engine is CUDA-only; there is no CPU fallback)")
+        lib = C.CDLL(p)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        if lib.mcr_abi_version() != 1:
+            raise RuntimeError("libmcr_b200.so ABI version mismatch")
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def _ptr(t: Any) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return int(t.data_ptr())
+
+
+def _stream_handle() -> Optional[int]:
+    import torch
+
+    return int(torch.cuda.current_stream().cuda_stream) or None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Context:
+    """One mcr_ctx (one simulator instance, one device)."""
+
+    def __init__(self, params: Params, main_seed: int, device: int = 0):
+        self.lib = load_library()
+        self.params = params
+        self.device = device
+        h = _VP()
+        rc = self.lib.mcr_create(C.byref(params), C.c_uint64(main_seed & 0xFFFFFFFFFFFFFFFF), device, C.byref(h))
+        if rc != 0:
+            msg = self.lib.mcr_last_error(None).decode()
+            raise (ValueError if rc == E_INVAL else NativeError)(msg)
+        self.handle = h
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.mcr_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.mcr_last_error(self.handle).decode()
+            raise (ValueError if rc == E_INVAL else NativeError)(msg)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mcr_launch_count(self.handle))
+
+    # ---- timeline -------------------------------------------------------------------------
+    def simulate(self, seed_stream: int, working_months: int, first_path: int, n_paths: int, out: Outputs,
+                 strict: bool = False) -> None:
+        self._check(self.lib.mcr_simulate(self.handle, seed_stream, working_months, first_path, n_paths,
+                                          FLAG_STRICT if strict else 0, C.byref(out), _stream_handle()))
+
+    def replay(self, shocks, shocks_ld: int, n_months: int, working_months: int, n_paths: int, out: Outputs,
+               strict: bool = True) -> None:
+        self._check(self.lib.mcr_replay(self.handle, _ptr(shocks), shocks_ld, n_months, working_months, n_paths,
+                                        FLAG_STRICT if strict else 0, C.byref(out), _stream_handle()))
+
+    def single_path(self, working_months: int, shocks_np):
+        import numpy as np
+
+        sh = np.ascontiguousarray(shocks_np, dtype=np.float64)
+        if sh.ndim != 2 or sh.shape[1] != 3:
+            raise ValueError("shocks must have shape (n_months, 3)")
+        R = int(self.params.retirement_years)
+        T = int(self.lib.mcr_trajectory_len(working_months, R))
+        traj = np.empty(T)
+        real = np.empty(T)
+        wr = np.empty(R)
+        rec = PathRecord()
+        self._check(self.lib.mcr_single_path(self.handle, working_months, sh.ctypes.data, sh.shape[0], C.byref(rec),
+                                             traj.ctypes.data, real.ctypes.data, wr.ctypes.data))
+        return rec, traj, real, wr
+
+    def helper_withdraw(self, bal, cb, target, use_tax, rate):
+        out = (_D * 4)()
+        self._check(self.lib.mcr_helper_withdraw(self.handle, bal, cb, target, int(bool(use_tax)), rate, out))
+        return tuple(out)
+
+    def helper_net_liquidation(self, bal, cb, use_tax, rate) -> float:
+        out = _D()
+        self._check(self.lib.mcr_helper_net_liquidation(self.handle, bal, cb, int(bool(use_tax)), rate, C.byref(out)))
+        return out.value
+
+    def helper_rebalance(self, b1, cb1, b2, cb2):
+        out = (_D * 4)()
+        self._check(self.lib.mcr_helper_rebalance(self.handle, b1, cb1, b2, cb2, out))
+        return tuple(out)
+
+    def draw_shocks(self, seed_stream: int, first_path: int, n_paths: int, n_months: int, shocks, shocks_ld: int,
+                    strict: bool = False) -> None:
+        self._check(self.lib.mcr_draw_shocks(self.handle, seed_stream, first_path, n_paths, n_months,
+                                             FLAG_STRICT if strict else 0, _ptr(shocks), shocks_ld, _stream_handle()))
+
+    # ---- search ---------------------------------------------------------------------------
+    def search_batch(self, seed_stream: int, candidates: Sequence[int], first_path: int, n_paths: int, counts,
+                     executed=None, strict: bool = False) -> None:
+        arr = (_I32 * len(candidates))(*[int(c) for c in candidates])
+        self._check(self.lib.mcr_search_batch(self.handle, seed_stream, arr, len(candidates), first_path, n_paths,
+                                              FLAG_STRICT if strict else 0, _ptr(counts), _ptr(executed),
+                                              _stream_handle()))
+
+    # ---- aggregations -----------------------------------------------------------------------
+    def quantiles(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, counts=None, mask=None,
+                  median: bool = False) -> None:
+        qs = (_D * len(q))(*[float(v) for v in q])
+        self._check(self.lib.mcr_quantiles(self.handle, _ptr(values), n, ld, rows, _ptr(mask), qs, len(q),
+                                           SEL_MEDIAN if median else 0, _ptr(out), _ptr(counts), _stream_handle()))
+
+    def first_year_rates(self, start, fy_real, n: int, rates) -> None:
+        self._check(self.lib.mcr_first_year_rates(self.handle, _ptr(start), _ptr(fy_real), n, _ptr(rates),
+                                                  _stream_handle()))
+
+    def minmax(self, values, n: int, out2, mask=None, divisor: float = 1.0) -> None:
+        self._check(self.lib.mcr_minmax(self.handle, _ptr(values), _ptr(mask), n, divisor, _ptr(out2),
+                                        _stream_handle()))
+
+    def histogram(self, values, n: int, n_bins: int, range2, hist, mask=None, divisor: float = 1.0,
+                  mode: int = HIST_NUMPY) -> None:
+        self._check(self.lib.mcr_histogram(self.handle, _ptr(values), _ptr(mask), n, divisor, n_bins, mode,
+                                           _ptr(range2), _ptr(hist), _stream_handle()))
+
+    def gather_columns(self, series, ld: int, rows: int, cols: Sequence[int], out) -> None:
+        arr = (_I64 * len(cols))(*[int(c) for c in cols])
+        self._check(self.lib.mcr_gather_columns(self.handle, _ptr(series), ld, rows, arr, len(cols), _ptr(out),
+                                                _stream_handle()))
+
+    def fp64_peak_slots_per_s(self) -> float:
+        out = _D()
+        self._check(self.lib.mcr_fp64_peak_slots_per_s(self.handle, C.byref(out)))
+        return out.value

@@ -1,0 +1,48 @@
+"""Helpers shared by the GPU tests."""
+from __future__ import annotations
+
+import numpy as np
+
+REL = 1e-9  # north_star: per-path balances within 1e-9 relative in fp64
+
+
+def make_sim(cfg, **kw):
+    from monte_carlo_retirement_b200.config import Config
+    from monte_carlo_retirement_b200.simulation import RetirementMonteCarloSimulator
+
+    if isinstance(cfg, dict):
+        cfg = Config(**cfg)
+    return RetirementMonteCarloSimulator(cfg, **kw)
+
+
+def assert_close(got, want, rel=REL, abs_tol=1e-6):
+    """|got - want| <= rel * |want| + abs_tol * rel-scale. The absolute term only covers values
+    the engine itself snaps to zero (balances <= 1e-6 are zeroed by the reference)."""
+    got = np.asarray(got, dtype=float)
+    want = np.asarray(want, dtype=float)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = np.abs(got - want)
+    tol = rel * np.abs(want) + abs_tol * 1e-3
+    bad = ~(err <= tol)
+    if bad.any():
+        i = np.argwhere(bad)[0]
+        raise AssertionError(f"{bad.sum()} mismatches; first at {tuple(i)}: got {got[tuple(i)]!r} want "
+                             f"{want[tuple(i)]!r} (rel err {err[tuple(i)] / max(abs(want[tuple(i)]), 1e-300):.3e})")
+
+
+def device_batch_to_host(b):
+    cols = b.cols.cpu().numpy()
+    ruin = b.ruin.cpu().numpy()
+    counters = b.counters.cpu().numpy()
+    out = {
+        "start": cols[0], "final": cols[1], "fy_gross": cols[2], "fy_real": cols[3], "infl": cols[4],
+        "success": b.success.cpu().numpy().astype(bool),
+        "ruin_month": ruin,
+        "ruin_years": np.where(ruin < 0, np.nan, ruin / 12.0),
+        "success_count": counters[0], "executed": counters[1], "ruin_hist": counters[2:],
+    }
+    if b.traj is not None:
+        out["traj"] = b.traj.cpu().numpy().T.copy()  # -> (n, T) like the reference's lists
+        out["real"] = b.real.cpu().numpy().T.copy()
+        out["wr"] = b.wr.cpu().numpy().T.copy()
+    return out

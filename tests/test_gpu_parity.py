@@ -1,0 +1,183 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle and the
+golden vectors of the unmodified reference, on the same inputs.
+
+Bars (BASELINE.json north_star): replay of the reference's numpy draws -> bit-exact success
+flags / ruin months / NaN patterns, balances within 1e-9 relative (fp64). Helper arithmetic has
+no transcendental, so it is required to be bit-exact.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import golden_io
+import scenarios
+from gpu_util import REL, assert_close, device_batch_to_host, make_sim
+
+pytestmark = pytest.mark.gpu
+
+CASES = list(golden_io.iter_cases())
+IDS = [f"{n}-{c['stream']}-wm{c['wm']}" for n, _, _, c in CASES]
+
+
+def _shocks_device(sim, wm, seeds):
+    import torch
+
+    R = sim.params_model.retirement_years
+    n_rows = max(wm + 12 * R, 1)
+    host = np.empty((n_rows, 3, len(seeds)))
+    for i, s in enumerate(seeds):
+        host[:, :, i] = sim._draw_shock_path(n_rows, int(s))
+    return torch.from_numpy(host).to("cuda"), host
+
+
+@pytest.mark.parametrize("name,cfg,seed,case", CASES, ids=IDS)
+def test_replay_matches_reference_golden(name, cfg, seed, case):
+    """mcr_replay on the reference's own numpy draws vs the reference's recorded outputs."""
+    sim = make_sim(cfg)
+    wm, n = int(case["wm"]), int(case["n"])
+    shocks, host_shocks = _shocks_device(sim, wm, case["seeds"])
+    # guard: the numpy bit-stream here is the one the fixtures were made with
+    assert np.array_equal(np.vstack([host_shocks[:3, :, 0], host_shocks[-1:, :, 0]]), case["shock_probe"])
+    b = sim.run_batch_device(wm, n, shocks=shocks)
+    h = device_batch_to_host(b)
+    assert np.array_equal(h["success"], case["success"])                     # bit-exact flags
+    assert np.array_equal(np.isnan(h["ruin_years"]), np.isnan(case["ruin"]))
+    assert np.array_equal(np.nan_to_num(h["ruin_years"], nan=-1.0), np.nan_to_num(case["ruin"], nan=-1.0))
+    assert_close(h["start"], case["start"])
+    assert_close(h["final"], case["final"])
+    assert_close(h["fy_gross"], case["fy_gross"])
+    assert_close(h["fy_real"], case["fy_real"])
+    assert_close(h["infl"], case["infl"])
+    assert_close(h["traj"], case["traj"])
+    assert_close(h["real"], case["real"])
+    assert np.array_equal(np.isnan(h["wr"]), np.isnan(case["wr"]))
+    assert_close(np.nan_to_num(h["wr"]), np.nan_to_num(case["wr"]))
+    assert int(h["success_count"]) == int(case["success"].sum())
+
+
+@pytest.mark.parametrize("name,cfg,seed,case", CASES[::3], ids=IDS[::3])
+def test_replay_matches_oracle(name, cfg, seed, case):
+    """Same inputs through the C oracle (which is pinned bit-exact to the reference)."""
+    from oracle import oracle as orc
+
+    sim = make_sim(cfg)
+    wm, n = int(case["wm"]), int(case["n"])
+    shocks, host = _shocks_device(sim, wm, case["seeds"])
+    p = orc.params_from_config(cfg)
+    recs, traj, real, wr = orc.run_batch(p, wm, np.ascontiguousarray(host.transpose(2, 0, 1)))
+    h = device_batch_to_host(sim.run_batch_device(wm, n, shocks=shocks))
+    assert np.array_equal(h["success"], recs["success"].astype(bool))
+    assert_close(h["final"], recs["final_balance"])
+    assert_close(h["traj"], traj)
+    assert_close(h["real"], real)
+    assert np.array_equal(np.isnan(h["wr"]), np.isnan(wr))
+
+
+@pytest.mark.parametrize("name", ["config_json", "jorge_plus", "tax_heavy", "annual_both", "broke"])
+def test_single_path_matches_golden(name):
+    """`_run_single_simulation_path(wm, path_seed)` — the call 11 reference tests make."""
+    cfg, seed, cases = golden_io.load_paths(name)
+    sim = make_sim(cfg)
+    for case in cases:
+        for i in range(min(3, int(case["n"]))):
+            r = sim._run_single_simulation_path(int(case["wm"]), int(case["seeds"][i]))
+            assert r["Success"] is bool(case["success"][i])
+            assert_close(r["Start Balance"], case["start"][i])
+            assert_close(r["Final Balance"], case["final"][i])
+            assert_close(r["First Year Gross Withdrawal"], case["fy_gross"][i])
+            assert_close(r["First Year Real Gross Withdrawal"], case["fy_real"][i])
+            assert_close(r["Inflation At Retirement"], case["infl"][i])
+            assert_close(np.array(r["Trajectory"]), case["traj"][i])
+            assert_close(np.array(r["RealTrajectory"]), case["real"][i])
+            wr = np.array(r["WithdrawalRateTrajectory"])
+            assert np.array_equal(np.isnan(wr), np.isnan(case["wr"][i]))
+            assert_close(np.nan_to_num(wr), np.nan_to_num(case["wr"][i]))
+            g = case["ruin"][i]
+            assert (np.isnan(g) and np.isnan(r["YearsToRuin"])) or r["YearsToRuin"] == g
+
+
+def test_helpers_bit_exact_vs_reference():
+    """_calculate_withdrawal_and_update / _net_liquidation_value / _rebalance_portfolio: plain
+    IEEE arithmetic, so the strict CUDA thread must reproduce the reference bit for bit."""
+    z = golden_io.load_helpers()
+    sim = make_sim(scenarios.CONFIG_JSON)
+    for row, exp_wd, exp_nl in zip(z["wd_in"][::2], z["wd_out"][::2], z["nl_out"][::2]):
+        got = sim._calculate_withdrawal_and_update(row[0], row[1], row[2], bool(row[3]), row[4])
+        assert np.array_equal(np.array(got), exp_wd), (row, got, exp_wd)
+        assert sim._net_liquidation_value(row[0], row[1], bool(row[3]), row[4]) == exp_nl
+    cfgs = {"tax_heavy": scenarios.TAX_HEAVY, "config_json": scenarios.CONFIG_JSON,
+            "annual_both": scenarios.ANNUAL_BOTH, "test_base": scenarios.TEST_BASE}
+    for name in z["sim_names"]:
+        s = make_sim(cfgs[str(name)])
+        for row, exp in zip(z["rb_in"][::3], z[f"rb_{name}"][::3]):
+            got = s._rebalance_portfolio(row[0], row[1], row[2], row[3])
+            assert np.array_equal(np.array(got), exp), (name, row, got, exp)
+
+
+@pytest.mark.parametrize("name,cfg,seed,case", CASES[1::4], ids=IDS[1::4])
+def test_dropin_7tuple_numpy_rng_matches_reference(name, cfg, seed, case):
+    """run_monte_carlo_simulations with rng='numpy' against the reference's own 7-tuple: device
+    radix-select bands, sample paths, WR bands and observation counts."""
+    sim = make_sim(cfg, rng="numpy")
+    (sim.use_search_seeds if case["stream"] == "search" else sim.use_final_seeds)()
+    # same seeds as the fixture (the reference spawned them in fixture order on one simulator)
+    sim._path_seed_cache[(sim._stream_name, int(case["n"]))] = [int(s) for s in case["seeds"]]
+    summary, traj_pct, samples, wr_pct, real_pct, real_samples, wr_counts = sim.run_monte_carlo_simulations(
+        int(case["wm"]), int(case["n"]))
+    assert list(summary.columns) == ["Start Balance", "Final Balance", "Success", "YearsToRuin",
+                                     "First Year Gross Withdrawal", "First Year Real Gross Withdrawal",
+                                     "Inflation At Retirement"]
+    assert np.array_equal(summary["Success"].to_numpy(), case["success"])
+    assert summary["Success"].dtype == bool
+    assert_close(summary["Start Balance"].to_numpy(), case["start"])
+    assert_close(summary["Final Balance"].to_numpy(), case["final"])
+    assert list(traj_pct.columns) == list(case["pct_cols"]) and list(wr_pct.columns) == list(case["wr_cols"])
+    assert_close(traj_pct.to_numpy(), case["traj_pct"])
+    assert_close(real_pct.to_numpy(), case["real_pct"])
+    assert np.array_equal(np.isnan(wr_pct.to_numpy()), np.isnan(case["wr_pct"]))
+    assert_close(np.nan_to_num(wr_pct.to_numpy()), np.nan_to_num(case["wr_pct"]))
+    assert wr_counts == [int(v) for v in case["wr_counts"]]
+    assert_close(np.array(samples), case["samples"])
+    assert_close(np.array(real_samples), case["real_samples"])
+    assert traj_pct[0.5].shape[0] == len(case["traj_pct"])  # float column labels work like the reference's
+
+
+def test_search_numpy_rng_reproduces_reference_search():
+    """find_minimum_working_months on the reference's draws: same months, probability,
+    search_curve and probe order as the reference (config.json and a stressed scenario)."""
+    g = golden_io.load_search()
+    for name in ("jorge_json", "stressed", "unreachable"):
+        sim = make_sim(g[name]["cfg"], rng="numpy")
+        events = []
+        months, prob, curve = sim.find_minimum_working_months(verbose=False, progress_callback=events.append)
+        assert months == g[name]["months"]
+        assert prob == g[name]["prob"]
+        assert curve == g[name]["curve"]
+        assert events == g[name]["events"]
+
+
+def test_fast_and_strict_builds_agree_on_replay_inputs():
+    """The throughput build (FMA contraction, shared reciprocals, short-range exp) must stay
+    within 1e-9 relative of the parity build and produce the same success flags."""
+    import torch
+
+    for cfg, wm in ((scenarios.SYNTH_C3, 240), (scenarios.TAX_HEAVY, 150), (scenarios.JORGE_PLUS, 75),
+                    (scenarios.STRESSED, 60), (scenarios.ANNUAL_BOTH, 100)):
+        n = 4096
+        strict = make_sim(cfg, strict=True)
+        fast = make_sim(cfg, strict=False)
+        # identical draws for both builds: native strict draws, replayed by the strict kernel,
+        # against the fast kernel fed through its own Philox (same counters, MUFU normals differ
+        # by ~1e-6), so compare fast vs strict on the SAME shocks via a fast replay of them.
+        R = cfg["retirement_years"]
+        n_rows = wm + 12 * R
+        shocks = torch.empty((n_rows, 3, n), dtype=torch.float64, device="cuda")
+        strict.native_context.draw_shocks(1, 0, n, n_rows, shocks, n, strict=True)
+        hs = device_batch_to_host(strict.run_batch_device(wm, n, shocks=shocks))
+        hf = device_batch_to_host(fast.run_batch_device(wm, n, shocks=shocks, _fast_replay=True))
+        assert np.array_equal(hs["success"], hf["success"])
+        assert np.array_equal(hs["ruin_month"], hf["ruin_month"])
+        assert_close(hs["final"], hf["final"])
+        assert_close(hs["traj"], hf["traj"])
+        assert_close(hs["fy_real"], hf["fy_real"])
