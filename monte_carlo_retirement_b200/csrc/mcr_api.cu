@@ -25,6 +25,9 @@ struct mcr_ctx {
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
+  // live (positive-amount) streams in original order: eligibility age and duration in months
+  double live_start_age[MCR_MAX_STREAMS];
+  int32_t live_duration[MCR_MAX_STREAMS];
   // scratch (device), grown on demand
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -92,7 +95,8 @@ int32_t start_month_index(double current_age, int32_t wm, double start_at_age) {
   return k > 2147483647.0 ? 2147483647 : (int32_t)k;
 }
 
-int validate_and_derive(const mcr_params& p, DevParams& d, std::string& why) {
+int validate_and_derive(const mcr_params& p, DevParams& d, double* live_start_age, int32_t* live_duration,
+                        std::string& why) {
   auto bad = [&](const char* m) { why = m; return MCR_EINVAL; };
   if (!(p.initial_balance >= 0) || !(p.monthly_contribution >= 0) || !(p.monthly_expenses >= 0))
     return bad("balances, contributions and expenses must be >= 0");
@@ -136,16 +140,23 @@ int validate_and_derive(const mcr_params& p, DevParams& d, std::string& why) {
   d.growth_on = p.contribution_growth_rate_annual > 0;
   d.annual_any = (!d.use1 && d.ann1 > 0) || (!d.use2 && d.ann2 > 0);
   d.R = p.retirement_years;
-  d.n_streams = p.n_streams;
+  int live = 0;
   for (int k = 0; k < p.n_streams; ++k) {
     const mcr_income_stream& s = p.streams[k];
     if (!(s.monthly_amount_today >= 0) || !(s.tax_rate >= 0 && s.tax_rate <= 1) || !(s.start_at_age >= 0))
       return bad("bad other_income_streams entry");
-    d.streams[k].amount = s.monthly_amount_today;
-    d.streams[k].net_factor = 1.0 - s.tax_rate;                  // simulation.py:675-677
-    d.streams[k].duration = s.duration_years < 0 ? -1 : s.duration_years * MCR_MONTHS_PER_YEAR;
-    d.streams[k].indexed = s.inflation_indexed != 0;
+    // a zero amount pays nominal 0.0 and adds +0.0 to the income sum (exact); a zero duration
+    // is never active (simulation.py:653-656): neither can change any result.
+    if (s.monthly_amount_today == 0.0 || s.duration_years == 0) continue;
+    d.streams[live].amount = s.monthly_amount_today;
+    d.streams[live].net_factor = 1.0 - s.tax_rate;               // simulation.py:675-677
+    d.streams[live].duration = s.duration_years < 0 ? -1 : s.duration_years * MCR_MONTHS_PER_YEAR;
+    d.streams[live].indexed = s.inflation_indexed != 0;
+    live_start_age[live] = s.start_at_age;
+    live_duration[live] = d.streams[live].duration;
+    ++live;
   }
+  d.n_streams = live;
   return MCR_OK;
 }
 
@@ -157,9 +168,18 @@ int check_months(mcr_ctx* ctx, int32_t wm) {
   return MCR_OK;
 }
 
-void fill_start_months(const mcr_ctx* ctx, int32_t wm, int32_t* out) {
-  for (int k = 0; k < MCR_MAX_STREAMS; ++k)
-    out[k] = k < ctx->params.n_streams ? start_month_index(ctx->params.current_age, wm, ctx->params.streams[k].start_at_age) : 0;
+// per live stream: [first paying retirement month, end) — simulation.py:602-621,653-656
+void fill_windows(const mcr_ctx* ctx, int32_t wm, int32_t* out) {
+  for (int k = 0; k < MCR_MAX_STREAMS; ++k) {
+    int32_t first = 0, end = 0;
+    if (k < ctx->dev.n_streams) {
+      first = start_month_index(ctx->params.current_age, wm, ctx->live_start_age[k]);
+      const int64_t e = ctx->live_duration[k] < 0 ? 2147483647ll : (int64_t)first + ctx->live_duration[k];
+      end = e > 2147483647ll ? 2147483647 : (int32_t)e;
+    }
+    out[2 * k] = first;
+    out[2 * k + 1] = end;
+  }
 }
 
 }  // namespace
@@ -184,7 +204,9 @@ int mcr_create(const mcr_params* params, uint64_t main_seed, int device, mcr_ctx
   *out_ctx = nullptr;
   DevParams d;
   std::string why;
-  if (validate_and_derive(*params, d, why) != MCR_OK) return fail(nullptr, MCR_EINVAL, why);
+  double live_age[MCR_MAX_STREAMS] = {0};
+  int32_t live_dur[MCR_MAX_STREAMS] = {0};
+  if (validate_and_derive(*params, d, live_age, live_dur, why) != MCR_OK) return fail(nullptr, MCR_EINVAL, why);
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0) {
@@ -203,6 +225,8 @@ int mcr_create(const mcr_params* params, uint64_t main_seed, int device, mcr_ctx
   ctx->sm_count = prop.multiProcessorCount;
   ctx->params = *params;
   ctx->dev = d;
+  std::memcpy(ctx->live_start_age, live_age, sizeof(live_age));
+  std::memcpy(ctx->live_duration, live_dur, sizeof(live_dur));
   ctx->main_seed = main_seed;
   const uint64_t key = splitmix64(splitmix64(main_seed) ^ 0x6D63725F62323030ull /* "mcr_b200" */);
   ctx->k0 = (uint32_t)key;
@@ -240,7 +264,7 @@ int mcr_simulate(mcr_ctx* ctx, int seed_stream, int32_t working_months, int64_t 
   A.wm = working_months;
   A.k0 = ctx->k0; A.k1 = ctx->k1; A.seed_stream = (uint32_t)seed_stream;
   A.first_path = first_path; A.n_paths = n_paths;
-  fill_start_months(ctx, working_months, A.start_month);
+  fill_windows(ctx, working_months, A.window);
   A.out = *out;
   MCR_CUDA(ctx, pick(flags).timeline(ctx->dev, A, false, (cudaStream_t)stream));
   ctx->launches += 1;
@@ -264,7 +288,7 @@ int mcr_replay(mcr_ctx* ctx, const double* shocks_dev, int64_t shocks_ld, int32_
   std::memset(&A, 0, sizeof(A));
   A.wm = working_months;
   A.n_paths = n_paths;
-  fill_start_months(ctx, working_months, A.start_month);
+  fill_windows(ctx, working_months, A.window);
   A.shocks = shocks_dev;
   A.shocks_ld = shocks_ld;
   A.out = *out;
@@ -302,7 +326,7 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
   std::memset(&A, 0, sizeof(A));
   A.wm = working_months;
   A.n_paths = 1;
-  fill_start_months(ctx, working_months, A.start_month);
+  fill_windows(ctx, working_months, A.window);
   A.shocks = d_sh;
   A.shocks_ld = 1;  // [(m*3 + c) * 1 + 0] == row-major (n_months, 3)
   A.out.start_balance = d_sc + 0;
@@ -402,7 +426,7 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
   std::stable_sort(order.begin(), order.end(),
                    [&](int a, int b) { return candidates_host[a] > candidates_host[b]; });
   const size_t per = (size_t)n_candidates;
-  std::vector<int32_t> h(per * (2 + MCR_MAX_STREAMS));
+  std::vector<int32_t> h(per * (2 + 2 * MCR_MAX_STREAMS));
   int32_t* h_wm = h.data();
   int32_t* h_slot = h_wm + per;
   int32_t* h_sm = h_slot + per;
@@ -410,7 +434,7 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
     const int c = order[k];
     h_wm[k] = candidates_host[c];
     h_slot[k] = c;
-    fill_start_months(ctx, candidates_host[c], h_sm + k * MCR_MAX_STREAMS);
+    fill_windows(ctx, candidates_host[c], h_sm + k * 2 * MCR_MAX_STREAMS);
   }
   if (int rc = ensure_scratch(ctx, h.size() * 4)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -423,7 +447,7 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
   A.first_path = first_path; A.n_paths = n_paths;
   A.wm = (const int32_t*)ctx->scratch;
   A.slot = A.wm + per;
-  A.start_month = A.slot + per;
+  A.window = A.slot + per;
   A.success_counts = success_counts_dev;
   A.executed_months = executed_months_dev;
   MCR_CUDA(ctx, pick(flags).search(ctx->dev, A, st));

@@ -14,7 +14,7 @@ struct TimelineArgs {
   int32_t wm;
   uint32_t k0, k1, seed_stream;   // Philox key words + seed stream (counter word 3)
   int64_t first_path, n_paths;
-  int32_t start_month[MCR_MAX_STREAMS];  // stream_payment_start_month_index per stream
+  int32_t window[2 * MCR_MAX_STREAMS];   // per live stream: first paying retirement month, end (exclusive)
   const double* shocks;           // replay only
   int64_t shocks_ld;
   mcr_outputs out;
@@ -26,7 +26,7 @@ struct SearchArgs {
   int64_t first_path, n_paths;
   const int32_t* wm;              // [n_candidates] device, sorted longest first
   const int32_t* slot;            // [n_candidates] device: index into the caller's arrays
-  const int32_t* start_month;     // [n_candidates][MCR_MAX_STREAMS] device
+  const int32_t* window;          // [n_candidates][2 * MCR_MAX_STREAMS] device
   int64_t* success_counts;        // caller buffer, accumulated
   uint64_t* executed_months;      // caller buffer or NULL, accumulated
 };

@@ -8,7 +8,10 @@
 
 namespace mcr {
 
-constexpr int kBlock = 128;  // 4 warps; ~120 regs/thread -> 4 CTAs (16 warps) per SM
+constexpr int kBlock = 128;  // 4 warps per CTA
+#ifndef MCR_MIN_BLOCKS
+#define MCR_MIN_BLOCKS 6     // resident CTAs per SM the register allocator must leave room for (80 regs)
+#endif
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
@@ -55,7 +58,7 @@ __device__ __forceinline__ void emit_outputs(const mcr_outputs& out, int64_t i, 
 }
 
 template <bool FAST, bool REPLAY>
-__global__ void __launch_bounds__(kBlock) k_timeline(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_timeline(const __grid_constant__ DevParams P,
                                                      const __grid_constant__ TimelineArgs A) {
   extern __shared__ uint32_t s_obs[];
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -70,12 +73,12 @@ __global__ void __launch_bounds__(kBlock) k_timeline(const __grid_constant__ Dev
     sink.wrp = A.out.wr_trajectory ? A.out.wr_trajectory + i : nullptr;
     if constexpr (REPLAY) {
       ReplayShock sh{A.shocks + i, A.shocks_ld};
-      run_timeline<FAST>(P, A.wm, A.start_month, sh, sink, o, years_observed);
+      run_timeline<FAST>(P, A.wm, A.window, sh, sink, o, years_observed);
     } else {
       const uint64_t gp = (uint64_t)(A.first_path + i);
       PhiloxShock<FAST> sh{A.k0, A.k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
                            P.rho_f, P.rho_c_f, P.rho, P.rho_c};
-      run_timeline<FAST>(P, A.wm, A.start_month, sh, sink, o, years_observed);
+      run_timeline<FAST>(P, A.wm, A.window, sh, sink, o, years_observed);
     }
   }
   emit_outputs(A.out, i, valid, o, years_observed, P.R, s_obs);
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kBlock) k_timeline(const __grid_constant__ Dev
 // of 128 paths. All 32 lanes of a warp share the candidate, so they fail at similar months;
 // no series, no per-path outputs: only the success count (and executed months) per candidate.
 template <bool FAST>
-__global__ void __launch_bounds__(kBlock) k_search(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ SearchArgs A) {
   const int c = blockIdx.y;
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kBlock) k_search(const __grid_constant__ DevPa
     const uint64_t gp = (uint64_t)(A.first_path + i);
     PhiloxShock<FAST> sh{A.k0, A.k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
                          P.rho_f, P.rho_c_f, P.rho, P.rho_c};
-    run_timeline<FAST>(P, A.wm[c], A.start_month + (size_t)c * MCR_MAX_STREAMS, sh, sink, o, years_observed);
+    run_timeline<FAST>(P, A.wm[c], A.window + (size_t)c * 2 * MCR_MAX_STREAMS, sh, sink, o, years_observed);
   }
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ok = __ballot_sync(0xffffffffu, valid && o.success);

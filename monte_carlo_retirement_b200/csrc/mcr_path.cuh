@@ -21,10 +21,13 @@ namespace mcr {
 constexpr double kEps = MCR_SMALL_EPSILON;
 constexpr int kMPY = MCR_MONTHS_PER_YEAR;
 
+// One income stream that can pay something. Streams with monthly_amount_today == 0 are dropped
+// on the host: they add +0.0 to the income sum, which is exact. The activity window
+// [first, end) of a stream depends on working_months and travels with the launch arguments.
 struct DevStream {
   double amount;        // monthly_amount_today
   double net_factor;    // 1.0 - tax_rate
-  int32_t duration;     // months, -1 == None
+  int32_t duration;     // months, -1 == None (informational; the window already encodes it)
   int32_t indexed;
 };
 
@@ -42,9 +45,25 @@ struct DevParams {
   int32_t growth_on;       // contribution_growth_rate_annual > 0
   int32_t annual_any;      // some asset can owe annual tax (needs the P&L accumulators)
   int32_t R;               // retirement_years
-  int32_t n_streams;
+  int32_t n_streams;       // streams with a positive amount, original order
   DevStream streams[MCR_MAX_STREAMS];
 };
+
+// income of one stream in retirement month r (simulation.py:650-677); `lock` holds the nominal
+// amount a non-indexed stream froze at its first payment (NaN-free sentinel: locked flag).
+__device__ __forceinline__ void stream_income(const DevStream& st, int first, int end, int r, double level0,
+                                              double& lock, bool& is_locked, double& income) {
+  if (r >= first && r < end) {
+    double nominal;
+    if (st.indexed) {
+      nominal = st.amount * level0;
+    } else {
+      if (!is_locked) { lock = st.amount * level0; is_locked = true; }
+      nominal = lock;
+    }
+    income += nominal * st.net_factor;
+  }
+}
 
 struct PathOut {
   double start_balance, final_balance, fy_gross, fy_real, infl_ret;
@@ -53,9 +72,25 @@ struct PathOut {
   uint32_t executed;   // months stepped (shock rows consumed)
 };
 
-// CPython max(a, b) / min(a, b): first argument wins ties and NaN compares.
-__device__ __forceinline__ double pmax(double a, double b) { return (b > a) ? b : a; }
-__device__ __forceinline__ double pmin(double a, double b) { return (b < a) ? b : a; }
+// CPython max(a, b) / min(a, b): first argument wins ties and NaN compares. Written as
+// setp + selp so the compiler cannot canonicalise them into fmax/fmin, whose NaN-correct SASS
+// expansion is 6 instructions instead of DSETP + 2 SEL.
+__device__ __forceinline__ double pmax(double a, double b) {
+  double d;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(d) : "d"(a), "d"(b));
+  return d;
+}
+__device__ __forceinline__ double pmin(double a, double b) {
+  double d;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(d) : "d"(a), "d"(b));
+  return d;
+}
+
+// exp(x) Taylor coefficients 1/13! .. 1/2! — constant-bank operands of the DFMAs (no UMOV pairs)
+static __constant__ double kExpC[12] = {
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
 
 // ---------------------------------------------------------------------------------------------
 // math policy
@@ -84,19 +119,10 @@ struct Math {
       // degree-13 Taylor polynomial on the unreduced argument (truncation < 3e-18 relative at
       // |x| = 0.34, 13 DFMA instead of the library's 17 FP64 ops + range reduction), with the
       // general routine as the (warp-rare) fallback.
-      if (fabs(x) < 0.34) {
-        double p = 1.6059043836821613e-10;              // 1/13!
-        p = fma(p, x, 2.08767569878681e-09);            // 1/12!
-        p = fma(p, x, 2.505210838544172e-08);           // 1/11!
-        p = fma(p, x, 2.755731922398589e-07);           // 1/10!
-        p = fma(p, x, 2.7557319223985893e-06);           // 1/9!
-        p = fma(p, x, 2.48015873015873e-05);            // 1/8!
-        p = fma(p, x, 1.984126984126984e-04);           // 1/7!
-        p = fma(p, x, 1.388888888888889e-03);           // 1/6!
-        p = fma(p, x, 8.333333333333333e-03);           // 1/5!
-        p = fma(p, x, 4.1666666666666664e-02);           // 1/4!
-        p = fma(p, x, 1.6666666666666666e-01);           // 1/3!
-        p = fma(p, x, 0.5);
+      if (__builtin_expect(fabs(x) < 0.34, 1)) {
+        double p = kExpC[0];
+#pragma unroll
+        for (int i = 1; i < 12; ++i) p = fma(p, x, kExpC[i]);
         p = fma(p, x, 1.0);
         return fma(p, x, 1.0);
       }
@@ -110,21 +136,27 @@ struct Math {
 // ---------------------------------------------------------------------------------------------
 // helpers — simulation.py:201-450. FULL = also maintain the cost basis of an untaxed asset
 // (needed only by the helper entry points that RETURN the basis).
+//
+// Clamps the reference writes but that are identities under the engine's invariants
+// (bal >= 0, cost basis >= 0, 0 <= rate <= 1, correctly rounded IEEE ops) are dropped; each is
+// annotated "identity:" with the reason. They return their second argument unchanged, so the
+// results stay bit-identical (the helper parity tests are bit-exact on random inputs, including
+// basis-above-market cases).
 // ---------------------------------------------------------------------------------------------
 
 // _net_liquidation_value — simulation.py:256-272
 __device__ __forceinline__ double net_liq(double bal, double cb, bool taxed, double rate) {
-  if (bal <= kEps) return 0.0;
-  if (!taxed) return pmax(0.0, bal);  // tax == 0.0, bal - 0.0 == bal
+  if (!taxed) return bal > kEps ? bal : 0.0;   // tax == 0.0; identity: max(0, bal - 0.0) with bal > eps
   const double gain = pmax(0.0, bal - cb);
-  return pmax(0.0, bal - gain * rate);
+  // identity: max(0, bal - gain*rate): gain <= bal and rate <= 1, so the difference is >= +0.0
+  return bal > kEps ? bal - gain * rate : 0.0;
 }
 
 // _calculate_withdrawal_and_update — simulation.py:201-254
 template <bool FAST, bool FULL>
 __device__ __forceinline__ void withdraw(double& bal, double& cb, double target, bool taxed, double rate,
                                          double& gross, double& net) {
-  if (bal <= kEps || target <= 0) {  // :218-219
+  if (__builtin_expect(bal <= kEps || target <= 0, 0)) {  // :218-219
     bal = pmax(0.0, bal);
     cb = pmax(0.0, cb);
     gross = 0.0;
@@ -134,33 +166,33 @@ __device__ __forceinline__ void withdraw(double& bal, double& cb, double target,
   if (!taxed && !FULL) {
     // effective tax fraction 0 -> net_fraction == 1.0, target / 1.0 == target, tax_paid == 0.
     gross = pmin(target, bal);
-    net = pmax(0.0, gross);
-    double nb = pmax(0.0, bal - gross);
+    net = gross;                       // identity: max(0, gross - 0.0), gross > 0
+    double nb = bal - gross;           // identity: max(0, bal - gross), gross <= bal
     if (nb <= kEps) nb = 0.0;
     bal = nb;
     return;  // cost basis of an untaxed asset is dead state
   }
-  double gf, fs;
+  double fs;
   if constexpr (FAST) {
     const double rb = Math<FAST>::rcp(bal);
-    gf = pmax(0.0, bal - cb) * rb;
+    const double gf = pmax(0.0, bal - cb) * rb;
     const double etf = taxed ? gf * rate : 0.0;
     const double nf = pmax(kEps, 1.0 - etf);
     gross = pmin(target * Math<FAST>::rcp(nf), bal);
-    fs = pmin(1.0, gross * rb);
+    fs = pmin(1.0, gross * rb);        // the approximate reciprocal may land 1 ulp above 1
   } else {
-    gf = pmax(0.0, bal - cb) / bal;                      // :221
+    const double gf = pmax(0.0, bal - cb) / bal;         // :221
     const double etf = taxed ? gf * rate : 0.0;          // :222-226
     const double nf = pmax(kEps, 1.0 - etf);             // :227
     gross = pmin(target / nf, bal);                      // :228-231
-    fs = pmin(1.0, gross / bal);                         // :233
+    fs = gross / bal;                  // :233 identity: min(1, gross/bal), gross <= bal
   }
-  const double br = pmin(cb, cb * fs);                   // :234
+  const double br = cb * fs;           // :234 identity: min(cb, cb*fs), fs <= 1
   const double tg = pmax(0.0, gross - br);               // :235
   const double tax = taxed ? tg * rate : 0.0;            // :236-240
-  net = pmax(0.0, gross - tax);                          // :241
-  double nb = pmax(0.0, bal - gross);                    // :243
-  double ncb = pmax(0.0, cb - br);                       // :244
+  net = gross - tax;                   // :241 identity: max(0, .), tax <= tg <= gross
+  double nb = bal - gross;             // :243 identity: max(0, .), gross <= bal
+  double ncb = cb - br;                // :244 identity: max(0, .), br <= cb
   if (nb <= kEps) { nb = 0.0; ncb = 0.0; }               // :245-247
   bal = nb;
   cb = ncb;
@@ -172,48 +204,50 @@ __device__ __forceinline__ void withdraw(double& bal, double& cb, double target,
 template <bool FAST, bool FULL>
 __device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
   const double total = b1 + b2;
-  if (total <= kEps) return;                              // :290-291
   const double drift1 = b1 - total * P.a1;                // :293-294
-  if (fabs(drift1) <= kEps) return;                       // :295-296
+  if (__builtin_expect(total <= kEps || fabs(drift1) <= kEps, 0)) return;   // :290-291, :295-296
   const bool sell1 = drift1 > 0;
   const double drift2 = b2 - total * P.a2;                // :328 (recomputed, not -drift1)
   const double bs = sell1 ? b1 : b2;
-  const double cbs = sell1 ? cb1 : cb2;
   const double bo = sell1 ? b2 : b1;
-  const double cbo = sell1 ? cb2 : cb1;
   const double drift = sell1 ? drift1 : drift2;
-  double sale, br = 0.0, buy;
   // the rebalance consults only the `use` flag (:302-306); use && rate == 0 gives tpd == 0.0
   // exactly, so `taxed` decides the arithmetic in both cases.
-  const bool both_plain = !P.taxed1 && !P.taxed2 && !FULL;
-  if (both_plain) {
-    sale = pmin(bs, drift);          // denominator == max(eps, 1.0 - a*0.0) == 1.0
-    buy = sale;                      // tax_paid == 0.0
-  } else {
-    const double rate = sell1 ? (P.use1 ? P.rate1 : 0.0) : (P.use2 ? P.rate2 : 0.0);
-    const double as = sell1 ? P.a1 : P.a2;
-    double fs;
-    if constexpr (FAST) {
-      const double rb = Math<FAST>::rcp(bs);
-      const double gf = pmax(0.0, bs - cbs) * rb;
-      const double den = pmax(kEps, 1.0 - as * (gf * rate));
-      sale = pmin(bs, drift * Math<FAST>::rcp(den));
-      fs = sale * rb;
-    } else {
-      const double gf = pmax(0.0, bs - cbs) / bs;           // :301 / :329
-      const double den = pmax(kEps, 1.0 - as * (gf * rate)); // :302-310
-      sale = pmin(bs, drift / den);                         // :311
-      fs = sale / bs;                                       // :312
-    }
-    br = pmin(cbs, cbs * fs);                               // :313
-    const double tg = pmax(0.0, sale - br);                 // :314
-    buy = sale - tg * rate;                                 // :315-320
+  if (!P.taxed1 && !P.taxed2 && !FULL) {
+    const double sale = pmin(bs, drift);   // denominator == max(eps, 1.0 - a*0.0) == 1.0; tax_paid == 0.0
+    double nbs = bs - sale;                // identity: max(0, .), sale <= bs
+    double nbo = bo + sale;
+    if (nbs <= kEps) nbs = 0.0;            // :355-358
+    if (nbo <= kEps) nbo = 0.0;
+    b1 = sell1 ? nbs : nbo;
+    b2 = sell1 ? nbo : nbs;
+    return;
   }
-  double nbs = pmax(0.0, bs - sale);                        // :322
-  double ncbs = pmax(0.0, cbs - br);                        // :323
-  double nbo = bo + buy;                                    // :324
-  double ncbo = cbo + buy;                                  // :325
-  if (nbs <= kEps) { nbs = 0.0; ncbs = 0.0; }               // :355-358
+  const double cbs = sell1 ? cb1 : cb2;
+  const double cbo = sell1 ? cb2 : cb1;
+  const double rate = sell1 ? (P.use1 ? P.rate1 : 0.0) : (P.use2 ? P.rate2 : 0.0);
+  const double as = sell1 ? P.a1 : P.a2;
+  double sale, fs;
+  if constexpr (FAST) {
+    const double rb = Math<FAST>::rcp(bs);
+    const double gf = pmax(0.0, bs - cbs) * rb;
+    const double den = pmax(kEps, 1.0 - as * (gf * rate));
+    sale = pmin(bs, drift * Math<FAST>::rcp(den));
+    fs = pmin(1.0, sale * rb);
+  } else {
+    const double gf = pmax(0.0, bs - cbs) / bs;           // :301 / :329
+    const double den = pmax(kEps, 1.0 - as * (gf * rate)); // :302-310
+    sale = pmin(bs, drift / den);                         // :311
+    fs = sale / bs;                                       // :312
+  }
+  const double br = cbs * fs;                             // :313 identity: min(cb, cb*fs), fs <= 1
+  const double tg = pmax(0.0, sale - br);                 // :314
+  const double buy = sale - tg * rate;                    // :315-320
+  double nbs = bs - sale;                                 // :322 identity: max(0, .), sale <= bs
+  double ncbs = cbs - br;                                 // :323 identity: max(0, .), br <= cbs
+  double nbo = bo + buy;                                  // :324
+  double ncbo = cbo + buy;                                // :325
+  if (nbs <= kEps) { nbs = 0.0; ncbs = 0.0; }             // :355-358
   if (nbo <= kEps) { nbo = 0.0; ncbo = 0.0; }
   b1 = sell1 ? nbs : nbo;
   cb1 = sell1 ? ncbs : ncbo;
@@ -224,24 +258,29 @@ __device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double
 // _apply_annual_gain_taxes — simulation.py:361-450. Returns tax_failed.
 template <bool FAST, bool FULL>
 __device__ __forceinline__ bool annual_tax(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2,
-                                           double g1, double g2) {
-  const double due1 = !P.use1 ? pmax(0.0, g1) * P.ann1 : 0.0;   // :380-384
-  const double due2 = !P.use2 ? pmax(0.0, g2) * P.ann2 : 0.0;   // :385-389
-  const double due = due1 + due2;
-  const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);      // :392-403
-  const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
-  const double cap = cap1 + cap2;
-  const double pay = pmin(due, cap);                            // :405
-  bool failed = pay < due - kEps;                               // :406
-  if (cap > kEps && pay > 0) {                                  // :408-430
-    const double share1 = cap1 / cap;
-    const double share2 = 1.0 - share1;
-    double gw, n1, n2;
-    withdraw<FAST, FULL>(b1, cb1, pay * share1, P.taxed1, P.rate1, gw, n1);
-    withdraw<FAST, FULL>(b2, cb2, pay * share2, P.taxed2, P.rate2, gw, n2);
-    if (n1 + n2 < due - kEps) failed = true;
+                                        double g1, double g2) {
+  bool failed = false;
+  if (P.annual_any) {
+    const double due1 = !P.use1 ? pmax(0.0, g1) * P.ann1 : 0.0;   // :380-384
+    const double due2 = !P.use2 ? pmax(0.0, g2) * P.ann2 : 0.0;   // :385-389
+    const double due = due1 + due2;
+    const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);      // :392-403
+    const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
+    const double cap = cap1 + cap2;
+    const double pay = pmin(due, cap);                            // :405
+    failed = pay < due - kEps;                                    // :406
+    if (cap > kEps && pay > 0) {                                  // :408-430
+      const double share1 = cap1 / cap;
+      const double share2 = 1.0 - share1;
+      double gw, n1, n2;
+      withdraw<FAST, FULL>(b1, cb1, pay * share1, P.taxed1, P.rate1, gw, n1);
+      withdraw<FAST, FULL>(b2, cb2, pay * share2, P.taxed2, P.rate2, gw, n2);
+      if (n1 + n2 < due - kEps) failed = true;
+    }
   }
-  rebalance<FAST, FULL>(P, b1, cb1, b2, cb2);                   // :432-442
+  // else: no asset can owe annual tax -> due == 0.0, pay == min(0.0, cap) == 0.0, nothing is
+  // sold and tax_failed is False; only the trailing rebalance of :432-442 runs.
+  rebalance<FAST, FULL>(P, b1, cb1, b2, cb2);                     // :432-442
   return failed;
 }
 
@@ -275,7 +314,7 @@ struct SeriesSink {
 // ---------------------------------------------------------------------------------------------
 template <bool FAST, class Shock, class Sink>
 __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
-                                             const int32_t* __restrict__ start_month, Shock& shock,
+                                             const int32_t* __restrict__ window, Shock& shock,
                                              Sink& sink, PathOut& o, int& years_observed) {
   const int R = P.R;
   double b1 = P.B0 * P.a1;                                   // :499-502
@@ -324,8 +363,12 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
   const double level_ret = level;
   if (wm > 0 && moy != 0) sink.point(t++, S0, level_ret);          // :590-594
 
-  double locked[MCR_MAX_STREAMS];
-  uint32_t locked_mask = 0;
+  // lock state of non-indexed streams: the first two live in registers, the rest in local memory
+  double lock0 = 0.0, lock1 = 0.0;
+  bool locked0 = false, locked1 = false;
+  double lockn[MCR_MAX_STREAMS];
+  uint32_t lockn_mask = 0;
+  const int ns = P.n_streams;
   double fy_gross = 0.0, fy_real = 0.0;
   bool ok = !pre_fail;                                             // :627-629
   int ruin = pre_fail ? 0 : -1;
@@ -341,23 +384,15 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
     for (int j = 0; j < kMPY; ++j, ++r) {
       const double level0 = level;                                 // :644-647
       const double need_nominal = P.E * level0;
-      double income = 0.0;
-      for (int k = 0; k < P.n_streams; ++k) {                      // :650-677
-        const int s0 = start_month[k];
-        const int dur = P.streams[k].duration;
-        const bool active = r >= s0 && (dur < 0 || r < s0 + dur);
-        if (!active) continue;
-        double nominal;
-        if (P.streams[k].indexed) {
-          nominal = P.streams[k].amount * level0;
-        } else {
-          if (!(locked_mask & (1u << k))) {
-            locked[k] = P.streams[k].amount * level0;
-            locked_mask |= 1u << k;
-          }
-          nominal = locked[k];
-        }
-        income += nominal * P.streams[k].net_factor;
+      double income = 0.0;                                         // :649-677
+      if (ns > 0) stream_income(P.streams[0], window[0], window[1], r, level0, lock0, locked0, income);
+      if (ns > 1) stream_income(P.streams[1], window[2], window[3], r, level0, lock1, locked1, income);
+      for (int k = 2; k < ns; ++k) {
+        bool lk = (lockn_mask >> k) & 1u;
+        double lv = lk ? lockn[k] : 0.0;
+        const bool was = lk;
+        stream_income(P.streams[k], window[2 * k], window[2 * k + 1], r, level0, lv, lk, income);
+        if (lk && !was) { lockn[k] = lv; lockn_mask |= 1u << k; }
       }
       const double need = pmax(0.0, need_nominal - income);        // :679-682
       if (b1 + b2 <= kEps && need > kEps) { failed = true; break; }  // :684-690
@@ -385,7 +420,7 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
       const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);     // :726-737
       const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
       const double cap = cap1 + cap2;
-      const double target = pmax(0.0, pmin(need, cap));            // :739-742
+      const double target = pmin(need, cap);   // :739-742 identity: max(0, .), need >= +0.0 and cap >= +0.0
       if (need > kEps && target < need - kEps) failed = true;      // :743-748
       const double w1 = cap > kEps ? cap1 / cap : P.a1;            // :750-755
       const double w2 = 1.0 - w1;
