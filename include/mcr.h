@@ -234,6 +234,28 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
                   const uint8_t* mask_dev, const double* q_host, int32_t n_q, uint32_t sel_flags,
                   double* out_dev, int64_t* counts_dev, void* stream);
 
+/* The same select one step at a time, for path shards spread over several GPUs:
+ *   BEGIN; for pass in 0..7 { if pass == mcr_select_full_passes(): COLLECT ;
+ *   HIST (local shard) ; all-reduce(sum) hist_dev across ranks ; ADVANCE } ; FINISH.
+ * (COLLECT gathers the local elements that share a resolved prefix into a short candidate list
+ * so the remaining digits do not rescan the rows.)
+ * After the all-reduce every rank holds the GLOBAL digit histogram, so all ranks walk to the
+ * same exact global order statistics without moving any path data. state_dev / hist_dev are
+ * caller-owned device buffers of mcr_select_state_bytes(rows) / mcr_select_hist_bytes(rows)
+ * bytes; hist_dev is an array of uint32 counts (all-reduce it as int32). */
+#define MCR_SELECT_BEGIN 0
+#define MCR_SELECT_HIST 1
+#define MCR_SELECT_ADVANCE 2
+#define MCR_SELECT_FINISH 3
+#define MCR_SELECT_COLLECT 4
+int32_t mcr_select_full_passes(void);
+int64_t mcr_select_state_bytes(int32_t rows);
+int64_t mcr_select_hist_bytes(int32_t rows);
+int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const double* values_dev, int64_t n,
+                    int64_t ld, int32_t rows, const uint8_t* mask_dev, const double* q_host,
+                    int32_t n_q, uint32_t sel_flags, void* state_dev, void* hist_dev,
+                    double* out_dev, int64_t* counts_dev, void* stream);
+
 /* rates[i] = first_year_real[i] / start[i] * 100 where start[i] > 1e-6 else NaN
  * (median_first_year_withdrawal_rate, backend/simulation.py:78-96). */
 int mcr_first_year_rates(mcr_ctx* ctx, const double* start_dev, const double* first_year_real_dev,

@@ -455,14 +455,8 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
   return MCR_OK;
 }
 
-int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld, int32_t rows, const uint8_t* mask_dev,
-                  const double* q_host, int32_t n_q, uint32_t sel_flags, double* out_dev, int64_t* counts_dev,
-                  void* stream) {
-  if (!ctx || !values_dev || !out_dev) return fail(ctx, MCR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+static int make_spec(mcr_ctx* ctx, const double* q_host, int32_t n_q, uint32_t sel_flags, QuantileSpec& spec) {
   if (n_q <= 0 || n_q > kMaxQuantiles) return fail(ctx, MCR_EINVAL, "n_q must be in [1,16]");
-  if (n < 0 || rows < 0 || (rows > 1 && ld < n)) return fail(ctx, MCR_EINVAL, "bad shape");
-  QuantileSpec spec;
   std::memset(&spec, 0, sizeof(spec));
   spec.n_q = n_q;
   spec.median = (sel_flags & MCR_SEL_MEDIAN) ? 1 : 0;
@@ -471,14 +465,68 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
     if (!(spec.q[k] >= 0.0 && spec.q[k] <= 1.0)) return fail(ctx, MCR_EINVAL, "quantiles must be in [0,1]");
     if (k > 0 && spec.q[k] < spec.q[k - 1]) return fail(ctx, MCR_EINVAL, "quantiles must be ascending");
   }
+  return MCR_OK;
+}
+
+int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld, int32_t rows, const uint8_t* mask_dev,
+                  const double* q_host, int32_t n_q, uint32_t sel_flags, double* out_dev, int64_t* counts_dev,
+                  void* stream) {
+  if (!ctx || (!values_dev && n > 0) || !out_dev) return fail(ctx, MCR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n < 0 || rows < 0 || (rows > 1 && ld < n)) return fail(ctx, MCR_EINVAL, "bad shape");
+  QuantileSpec spec;
+  if (int rc = make_spec(ctx, q_host, n_q, sel_flags, spec)) return rc;
   if (rows == 0) return MCR_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
-  if (int rc = ensure_scratch(ctx, quantile_workspace_bytes(rows))) return rc;
+  const size_t hb = quantile_hist_bytes(rows);
+  if (int rc = ensure_scratch(ctx, hb + quantile_state_bytes(rows))) return rc;
   int n_launches = 0;
-  MCR_CUDA(ctx, launch_quantiles(values_dev, n, ld, rows, mask_dev, spec, out_dev, counts_dev, ctx->scratch,
-                                 (cudaStream_t)stream, &n_launches));
+  MCR_CUDA(ctx, launch_quantiles(values_dev, n, ld, rows, mask_dev, spec, out_dev, counts_dev,
+                                 (char*)ctx->scratch + hb, ctx->scratch, (cudaStream_t)stream, &n_launches));
   ctx->launches += n_launches;
+  return MCR_OK;
+}
+
+int64_t mcr_select_state_bytes(int32_t rows) { return (int64_t)quantile_state_bytes(rows); }
+int64_t mcr_select_hist_bytes(int32_t rows) { return (int64_t)quantile_hist_bytes(rows); }
+int32_t mcr_select_full_passes(void) { return select_full_passes(); }
+
+int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const double* values_dev, int64_t n, int64_t ld,
+                    int32_t rows, const uint8_t* mask_dev, const double* q_host, int32_t n_q, uint32_t sel_flags,
+                    void* state_dev, void* hist_dev, double* out_dev, int64_t* counts_dev, void* stream) {
+  if (!ctx || !state_dev || !hist_dev) return fail(ctx, MCR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n < 0 || rows <= 0 || (rows > 1 && ld < n) || pass < 0 || pass > 7) return fail(ctx, MCR_EINVAL, "bad shape");
+  QuantileSpec spec;
+  if (int rc = make_spec(ctx, q_host, n_q, sel_flags, spec)) return rc;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (step) {
+    case MCR_SELECT_BEGIN:
+      MCR_CUDA(ctx, launch_sel_begin(rows, state_dev, hist_dev, st));
+      break;
+    case MCR_SELECT_HIST:
+      if (!values_dev && n > 0) return fail(ctx, MCR_EINVAL, "null values");
+      MCR_CUDA(ctx, launch_sel_hist(values_dev, n, ld, rows, mask_dev, pass, state_dev, hist_dev, st));
+      break;
+    case MCR_SELECT_COLLECT:
+      if (!values_dev && n > 0) return fail(ctx, MCR_EINVAL, "null values");
+      MCR_CUDA(ctx, launch_sel_collect(values_dev, n, ld, rows, mask_dev, state_dev, st));
+      ctx->launches += 1;
+      break;
+    case MCR_SELECT_ADVANCE:
+      MCR_CUDA(ctx, launch_sel_advance(rows, spec, pass, state_dev, hist_dev, st));
+      break;
+    case MCR_SELECT_FINISH:
+      if (!out_dev) return fail(ctx, MCR_EINVAL, "null output");
+      MCR_CUDA(ctx, launch_sel_finish(rows, spec, state_dev, out_dev, counts_dev, st));
+      break;
+    default:
+      return fail(ctx, MCR_EINVAL, "bad select step");
+  }
+  ctx->launches += 1;
   return MCR_OK;
 }
 

@@ -40,50 +40,97 @@ __device__ __forceinline__ double value_of(uint64_t k) {
 // merge -> one small "advance" step) so that (a) a row is scanned by many SMs at once and (b) a
 // multi-GPU caller can all-reduce the merged histograms between the two halves of a pass and
 // obtain exact GLOBAL order statistics without moving any data.
+// Only the first three digits (24 key bits) are resolved by full scans of the row; a fourth scan
+// collects the (few) elements that share a live 24-bit prefix into a per-row candidate list and
+// the last five digits are resolved on that list. Rows whose candidates do not fit (masses of
+// identical values, e.g. zero-padded failed paths) keep scanning the full row.
+// Layout: the merged histograms live in their own contiguous array hist[rows][kMaxTargets][256]
+// (that is the buffer a multi-GPU caller all-reduces), the rest of the state in SelRow[rows].
 struct SelRow {
-  uint32_t hist[kMaxTargets][256];  // merged histogram of the current pass, per prefix group
   uint64_t prefix[kMaxTargets];     // per target (rank-sorted): key bits resolved so far
   int64_t rank[kMaxTargets];        // per target: rank inside the current prefix bucket
   uint64_t uprefix[kMaxTargets];    // sorted unique prefixes (groups) of the current pass
   int32_t group[kMaxTargets];       // target -> group
   int32_t slot[kMaxTargets];        // (quantile, lo/hi) -> rank-sorted target slot
   int32_t n_groups;
+  int32_t n_cand;                   // elements in this row's candidate list
+  int32_t overflow;                 // candidate list overflowed: keep scanning the full row
   int32_t pad_;
   int64_t n_valid;
 };
 
 constexpr int kHistThreads = 256;
-constexpr int kChunk = 16384;  // elements of one row handled by one CTA
+constexpr int kChunk = 16384;       // elements of one row handled by one CTA
+constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
+constexpr int kFullPasses = 3;      // digits resolved by full scans before the collect
+constexpr int kHistWords = kMaxTargets * 256;  // per row
 
-__global__ void k_sel_init(SelRow* __restrict__ rows) {
+__global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist) {
   SelRow& R = rows[blockIdx.x];
-  for (int k = threadIdx.x; k < kMaxTargets * 256; k += blockDim.x) (&R.hist[0][0])[k] = 0;
-  if (threadIdx.x == 0) { R.n_groups = 1; R.n_valid = 0; }
+  uint32_t* H = hist + (size_t)blockIdx.x * kHistWords;
+  for (int k = threadIdx.x; k < kHistWords; k += blockDim.x) H[k] = 0;
+  if (threadIdx.x == 0) { R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; }
 }
 
-// One pass: histogram of digit `pass` (MSB first) inside every live prefix bucket.
-__global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restrict__ values, int64_t n, int64_t ld,
-                                                           const uint8_t* __restrict__ mask, SelRow* __restrict__ rows,
-                                                           int pass) {
-  extern __shared__ uint32_t sh[];  // [n_groups][256] + uprefix copy
-  SelRow& R = rows[blockIdx.y];
-  const int ng = R.n_groups;
-  uint64_t* s_up = (uint64_t*)(sh + ng * 256);
-  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
-  if (pass > 0 && threadIdx.x < ng) s_up[threadIdx.x] = R.uprefix[threadIdx.x];
+// membership of a key's resolved-bits part among the live prefixes: a 256-entry table on the
+// last resolved digit (the most discriminating one) with chaining, instead of a binary search
+struct PrefixTable {
+  uint64_t up[kMaxTargets];
+  uint8_t head[256];          // group + 1, 0 == none
+  uint8_t next[kMaxTargets];  // chain
+};
+
+__device__ __forceinline__ void build_table(PrefixTable& T, const SelRow& R, int ng) {
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) T.head[k] = 0;
   __syncthreads();
-  const double* __restrict__ x = values + (int64_t)blockIdx.y * ld;
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < ng; ++g) {
+      const uint64_t u = R.uprefix[g];
+      T.up[g] = u;
+      T.next[g] = T.head[u & 255u];
+      T.head[u & 255u] = (uint8_t)(g + 1);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int lookup(const PrefixTable& T, uint64_t hi) {
+  int g = T.head[hi & 255u];
+  while (g) {
+    if (T.up[g - 1] == hi) return g - 1;
+    g = T.next[g - 1];
+  }
+  return -1;
+}
+
+// One pass: histogram of digit `pass` (MSB first) inside every live prefix bucket. Passes below
+// kFullPasses scan the row; later passes scan the row's candidate list unless it overflowed.
+__global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restrict__ values, int64_t n, int64_t ld,
+                                                           const uint8_t* __restrict__ mask,
+                                                           const SelRow* __restrict__ rows,
+                                                           uint32_t* __restrict__ hist,
+                                                           const double* __restrict__ cand, int pass) {
+  extern __shared__ uint32_t sh[];  // [n_groups][256]
+  __shared__ PrefixTable T;
+  const SelRow& R = rows[blockIdx.y];
+  const bool from_cand = pass >= kFullPasses && !R.overflow;
+  if (from_cand && blockIdx.x > 0) return;
+  const int ng = R.n_groups;
+  uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
+  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
+  if (pass > 0) build_table(T, R, ng); else __syncthreads();
+  const double* __restrict__ x = from_cand ? cand + (size_t)blockIdx.y * kCandCap : values + (int64_t)blockIdx.y * ld;
+  const uint8_t* __restrict__ m = from_cand ? nullptr : mask;
   const int shift = 56 - 8 * pass;
-  const int64_t begin = (int64_t)blockIdx.x * kChunk;
-  const int64_t end = begin + kChunk < n ? begin + kChunk : n;
-  const uint64_t up_lo = pass > 0 ? s_up[0] : 0, up_hi = pass > 0 ? s_up[ng - 1] : 0;
-  for (int64_t base = begin; base < end; base += kHistThreads * 4) {
+  const int64_t begin = from_cand ? 0 : (int64_t)blockIdx.x * kChunk;
+  const int64_t stop = from_cand ? (int64_t)R.n_cand : (begin + kChunk < n ? begin + kChunk : n);
+  for (int64_t base = begin; base < stop; base += kHistThreads * 4) {
     double v[4];
     bool ok[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {  // 4 independent loads in flight per thread
       const int64_t e = base + u * kHistThreads + threadIdx.x;
-      ok[u] = e < end && (!mask || mask[e]);
+      ok[u] = e < stop && (!m || m[e]);
       v[u] = ok[u] ? __ldcs(x + e) : 0.0;
     }
 #pragma unroll
@@ -91,22 +138,8 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restr
       int id = -1;
       if (ok[u] && v[u] == v[u]) {  // NaN never takes part (pandas skips it)
         const uint64_t k = key_of(v[u]);
-        int g = 0;
-        bool hit = true;
-        if (pass > 0) {
-          const uint64_t hi = k >> (shift + 8);
-          hit = false;
-          if (hi >= up_lo && hi <= up_hi) {
-            int lo_i = 0, hi_i = ng - 1;
-            while (lo_i <= hi_i) {
-              const int mid = (lo_i + hi_i) >> 1;
-              const uint64_t uu = s_up[mid];
-              if (uu == hi) { g = mid; hit = true; break; }
-              if (uu < hi) lo_i = mid + 1; else hi_i = mid - 1;
-            }
-          }
-        }
-        if (hit) id = g * 256 + (int)((k >> shift) & 255u);
+        const int g = pass > 0 ? lookup(T, k >> (shift + 8)) : 0;
+        if (g >= 0) id = g * 256 + (int)((k >> shift) & 255u);
       }
       // concentrated data puts whole warps in one bin: one atomic for the warp in that case
       const int id0 = __shfl_sync(0xffffffffu, id, 0);
@@ -119,71 +152,133 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restr
   }
   __syncthreads();
   for (int k = threadIdx.x; k < ng * 256; k += kHistThreads)
-    if (sh[k]) atomicAdd(&(&R.hist[0][0])[k], sh[k]);
+    if (sh[k]) atomicAdd(&H[k], sh[k]);
 }
 
-// Second half of a pass (one warp per row): consume the merged histogram.
-__global__ void k_sel_advance(SelRow* __restrict__ rows, QuantileSpec spec, int pass) {
+// After kFullPasses digits: gather the elements that share a live prefix into the row's list.
+__global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __restrict__ values, int64_t n, int64_t ld,
+                                                              const uint8_t* __restrict__ mask,
+                                                              SelRow* __restrict__ rows, double* __restrict__ cand) {
+  __shared__ PrefixTable T;
+  SelRow& R = rows[blockIdx.y];
+  build_table(T, R, R.n_groups);
+  const double* __restrict__ x = values + (int64_t)blockIdx.y * ld;
+  double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
+  const int shift = 64 - 8 * kFullPasses;
+  const int64_t begin = (int64_t)blockIdx.x * kChunk;
+  const int64_t stop = begin + kChunk < n ? begin + kChunk : n;
+  for (int64_t base = begin; base < stop; base += kHistThreads * 4) {
+    double v[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t e = base + u * kHistThreads + threadIdx.x;
+      ok[u] = e < stop && (!mask || mask[e]);
+      v[u] = ok[u] ? __ldcs(x + e) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (ok[u] && v[u] == v[u] && lookup(T, key_of(v[u]) >> shift) >= 0) {
+        const int at = atomicAdd(&R.n_cand, 1);
+        if (at < kCandCap) out[at] = v[u]; else R.overflow = 1;
+      }
+    }
+  }
+}
+
+__global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   SelRow& R = rows[blockIdx.x];
+  if (threadIdx.x == 0 && R.n_cand > kCandCap) { R.n_cand = kCandCap; R.overflow = 1; }
+}
+
+// Second half of a pass (one warp per target + housekeeping): consume the merged histogram.
+__global__ void __launch_bounds__(1024) k_sel_advance(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
+                                                      QuantileSpec spec, int pass) {
+  SelRow& R = rows[blockIdx.x];
+  uint32_t* H = hist + (size_t)blockIdx.x * kHistWords;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const int nq = spec.n_q, nt = 2 * nq;
   if (pass == 0) {
-    if (tid == 0) {
-      int64_t nv = 0;
-      for (int d = 0; d < 256; ++d) nv += R.hist[0][d];
-      R.n_valid = nv;
-      for (int q = 0; q < nq; ++q) {
-        int64_t lo = 0, hi = 0;
-        if (nv > 0) {
-          if (spec.median) {  // np.median: mean of the two middle order statistics
-            lo = (nv - 1) / 2;
-            hi = nv / 2;
-          } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
-            const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
-            if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
-            else if (vi < 0) { lo = hi = 0; }
-            else { lo = (int64_t)floor(vi); hi = lo + 1; }
+    if (warp == 0) {
+      int64_t part = 0;
+      for (int d = lane; d < 256; d += 32) part += H[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) {
+        const int64_t nv = part;
+        R.n_valid = nv;
+        for (int q = 0; q < nq; ++q) {
+          int64_t lo = 0, hi = 0;
+          if (nv > 0) {
+            if (spec.median) {  // np.median: mean of the two middle order statistics
+              lo = (nv - 1) / 2;
+              hi = nv / 2;
+            } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
+              const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
+              if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
+              else if (vi < 0) { lo = hi = 0; }
+              else { lo = (int64_t)floor(vi); hi = lo + 1; }
+            }
           }
+          R.rank[2 * q] = lo;
+          R.rank[2 * q + 1] = hi;
         }
-        R.rank[2 * q] = lo;
-        R.rank[2 * q + 1] = hi;
-      }
-      // rank-sort the targets (tiny insertion sort) so that prefixes stay sorted in every pass;
-      // for small n the (lo, hi) pairs of different quantiles interleave.
-      int32_t ord[kMaxTargets];
-      for (int t = 0; t < nt; ++t) ord[t] = t;
-      for (int i = 1; i < nt; ++i) {
-        const int32_t o = ord[i];
-        const int64_t r = R.rank[o];
-        int j = i - 1;
-        while (j >= 0 && R.rank[ord[j]] > r) { ord[j + 1] = ord[j]; --j; }
-        ord[j + 1] = o;
-      }
-      int64_t sorted[kMaxTargets];
-      for (int t = 0; t < nt; ++t) sorted[t] = R.rank[ord[t]];
-      for (int t = 0; t < nt; ++t) {
-        R.rank[t] = sorted[t];
-        R.slot[ord[t]] = t;
-        R.prefix[t] = 0;
-        R.group[t] = 0;
+        // rank-sort the targets (tiny insertion sort) so that prefixes stay sorted in every
+        // pass; for small n the (lo, hi) pairs of different quantiles interleave.
+        int32_t ord[kMaxTargets];
+        for (int t = 0; t < nt; ++t) ord[t] = t;
+        for (int i = 1; i < nt; ++i) {
+          const int32_t o = ord[i];
+          const int64_t r = R.rank[o];
+          int j = i - 1;
+          while (j >= 0 && R.rank[ord[j]] > r) { ord[j + 1] = ord[j]; --j; }
+          ord[j + 1] = o;
+        }
+        int64_t sorted[kMaxTargets];
+        for (int t = 0; t < nt; ++t) sorted[t] = R.rank[ord[t]];
+        for (int t = 0; t < nt; ++t) {
+          R.rank[t] = sorted[t];
+          R.slot[ord[t]] = t;
+          R.prefix[t] = 0;
+          R.group[t] = 0;
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  // each target walks its bucket histogram to the digit holding its rank
-  if (tid < nt && R.n_valid > 0) {
-    const uint32_t* h = R.hist[R.group[tid]];
-    int64_t r = R.rank[tid];
-    int d = 0;
-    for (; d < 255; ++d) {
-      const int64_t c = h[d];
-      if (r < c) break;
-      r -= c;
+  // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
+  // holding its rank
+  if (warp < nt && R.n_valid > 0) {
+    const uint32_t* h = H + R.group[warp] * 256;
+    uint32_t c[8];
+    uint32_t local = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; local += c[k]; }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
-    R.rank[tid] = r;
-    R.prefix[tid] = (R.prefix[tid] << 8) | (uint64_t)d;
+    const int64_t r = R.rank[warp];
+    const int64_t before = (int64_t)incl - local;
+    const bool mine = r >= before && r < (int64_t)incl;
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    if (who == 0) {  // rank beyond the bucket (cannot happen for consistent histograms): last bin
+      if (lane == 31) { R.rank[warp] = 0; R.prefix[warp] = (R.prefix[warp] << 8) | 255ull; }
+    } else if (lane == __ffs(who) - 1) {
+      int64_t rr = r - before;
+      int k = 0;
+      for (; k < 7; ++k) {
+        if (rr < (int64_t)c[k]) break;
+        rr -= c[k];
+      }
+      R.rank[warp] = rr;
+      R.prefix[warp] = (R.prefix[warp] << 8) | (uint64_t)(lane * 8 + k);
+    }
   }
-  __syncwarp();
+  __syncthreads();
   // groups of the next pass (targets are rank-sorted, so prefixes are sorted) + clear histograms
   if (tid == 0) {
     int g = 0;
@@ -193,8 +288,7 @@ __global__ void k_sel_advance(SelRow* __restrict__ rows, QuantileSpec spec, int 
     }
     R.n_groups = g < 1 ? 1 : g;
   }
-  __syncwarp();
-  for (int k = tid; k < kMaxTargets * 256; k += blockDim.x) (&R.hist[0][0])[k] = 0;
+  for (int k = tid; k < kHistWords; k += blockDim.x) H[k] = 0;
 }
 
 __global__ void k_sel_finish(const SelRow* __restrict__ rows, QuantileSpec spec, double* __restrict__ out,
@@ -361,30 +455,74 @@ cudaError_t launch_fp64_peak(int sm_count, int iters, double* sink, cudaStream_t
   return cudaGetLastError();
 }
 
-size_t quantile_workspace_bytes(int rows) { return sizeof(SelRow) * (size_t)(rows > 0 ? rows : 1); }
+size_t quantile_state_bytes(int rows) {
+  const size_t r = (size_t)(rows > 0 ? rows : 1);
+  return sizeof(SelRow) * r + sizeof(double) * kCandCap * r;  // state + candidate lists
+}
+size_t quantile_hist_bytes(int rows) { return sizeof(uint32_t) * kHistWords * (size_t)(rows > 0 ? rows : 1); }
+static double* cand_of(void* state, int rows) { return (double*)((char*)state + sizeof(SelRow) * (size_t)rows); }
 
-cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask,
-                             const QuantileSpec& spec, double* out, int64_t* counts, void* workspace, cudaStream_t st,
-                             int* n_launches) {
-  *n_launches = 0;
-  if (rows <= 0) return cudaSuccess;
-  SelRow* W = (SelRow*)workspace;
-  const unsigned chunks = (unsigned)((n + kChunk - 1) / kChunk);
-  const size_t smem = (size_t)kMaxTargets * 256 * sizeof(uint32_t) + kMaxTargets * sizeof(uint64_t);
-  k_sel_init<<<rows, 256, 0, st>>>(W);
-  ++*n_launches;
-  for (int pass = 0; pass < 8; ++pass) {
-    if (chunks > 0) {
-      k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>(values, n, ld, mask, W, pass);
-      ++*n_launches;
-    }
-    k_sel_advance<<<rows, 32, 0, st>>>(W, spec, pass);
-    ++*n_launches;
-  }
-  k_sel_finish<<<rows, 32, 0, st>>>(W, spec, out, counts);
-  ++*n_launches;
+cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st) {
+  if (rows > 0) k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist);
   return cudaGetLastError();
 }
+
+cudaError_t launch_sel_hist(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, int pass,
+                            void* state, void* hist, cudaStream_t st) {
+  const unsigned chunks = (unsigned)((n + kChunk - 1) / kChunk);
+  if (rows <= 0 || chunks == 0) return cudaSuccess;
+  const size_t smem = (size_t)kHistWords * sizeof(uint32_t);
+  k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>(values, n, ld, mask, (const SelRow*)state,
+                                                                       (uint32_t*)hist, cand_of(state, rows), pass);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sel_collect(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, void* state,
+                               cudaStream_t st) {
+  const unsigned chunks = (unsigned)((n + kChunk - 1) / kChunk);
+  if (rows <= 0) return cudaSuccess;
+  if (chunks > 0)
+    k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>(values, n, ld, mask, (SelRow*)state,
+                                                                         cand_of(state, rows));
+  k_sel_collect_finish<<<rows, 32, 0, st>>>((SelRow*)state);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sel_advance(int rows, const QuantileSpec& spec, int pass, void* state, void* hist, cudaStream_t st) {
+  if (rows > 0) k_sel_advance<<<rows, 32 * 2 * spec.n_q, 0, st>>>((SelRow*)state, (uint32_t*)hist, spec, pass);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sel_finish(int rows, const QuantileSpec& spec, const void* state, double* out, int64_t* counts,
+                              cudaStream_t st) {
+  if (rows > 0) k_sel_finish<<<rows, 32, 0, st>>>((const SelRow*)state, spec, out, counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask,
+                             const QuantileSpec& spec, double* out, int64_t* counts, void* state, void* hist,
+                             cudaStream_t st, int* n_launches) {
+  *n_launches = 0;
+  if (rows <= 0) return cudaSuccess;
+  cudaError_t e = launch_sel_begin(rows, state, hist, st);
+  ++*n_launches;
+  for (int pass = 0; pass < 8 && e == cudaSuccess; ++pass) {
+    if (pass == kFullPasses) {
+      e = launch_sel_collect(values, n, ld, rows, mask, state, st);
+      *n_launches += 1 + (n > 0);
+      if (e != cudaSuccess) break;
+    }
+    e = launch_sel_hist(values, n, ld, rows, mask, pass, state, hist, st);
+    *n_launches += n > 0;
+    if (e == cudaSuccess) e = launch_sel_advance(rows, spec, pass, state, hist, st);
+    ++*n_launches;
+  }
+  if (e == cudaSuccess) e = launch_sel_finish(rows, spec, state, out, counts, st);
+  ++*n_launches;
+  return e;
+}
+
+int select_full_passes() { return kFullPasses; }
 
 cudaError_t launch_rates(const double* start, const double* fy_real, int64_t n, double* rates, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -115,6 +115,11 @@ SIGNATURES = {
     "mcr_draw_shocks": (C.c_int, [_VP, C.c_int, _I64, _I64, _I32, _U32, _VP, _I64, _VP]),
     "mcr_search_batch": (C.c_int, [_VP, C.c_int, C.POINTER(_I32), _I32, _I64, _I64, _U32, _VP, _VP, _VP]),
     "mcr_quantiles": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, C.POINTER(_D), _I32, _U32, _VP, _VP, _VP]),
+    "mcr_select_state_bytes": (_I64, [_I32]),
+    "mcr_select_hist_bytes": (_I64, [_I32]),
+    "mcr_select_full_passes": (_I32, []),
+    "mcr_select_step": (C.c_int, [_VP, _I32, _I32, _VP, _I64, _I64, _I32, _VP, C.POINTER(_D), _I32, _U32, _VP, _VP,
+                                  _VP, _VP, _VP]),
     "mcr_first_year_rates": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP]),
     "mcr_minmax": (C.c_int, [_VP, _VP, _VP, _I64, _D, _VP, _VP]),
     "mcr_histogram": (C.c_int, [_VP, _VP, _VP, _I64, _D, _I32, _I32, _VP, _VP, _VP]),
@@ -261,6 +266,33 @@ class Context:
         qs = (_D * len(q))(*[float(v) for v in q])
         self._check(self.lib.mcr_quantiles(self.handle, _ptr(values), n, ld, rows, _ptr(mask), qs, len(q),
                                            SEL_MEDIAN if median else 0, _ptr(out), _ptr(counts), _stream_handle()))
+
+    def quantiles_distributed(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, all_reduce,
+                              counts=None, mask=None, median: bool = False) -> None:
+        """Exact GLOBAL quantiles over path shards held by several ranks: `all_reduce(tensor)`
+        must sum an int32 device tensor in place across ranks (torch.distributed.all_reduce)."""
+        import torch
+
+        dev = values.device
+        state = torch.empty(int(self.lib.mcr_select_state_bytes(rows)), dtype=torch.uint8, device=dev)
+        hist = torch.empty(int(self.lib.mcr_select_hist_bytes(rows)) // 4, dtype=torch.int32, device=dev)
+        qs = (_D * len(q))(*[float(v) for v in q])
+        flags = SEL_MEDIAN if median else 0
+
+        def step(kind, p=0):
+            self._check(self.lib.mcr_select_step(self.handle, kind, p, _ptr(values), n, ld, rows, _ptr(mask), qs,
+                                                 len(q), flags, _ptr(state), _ptr(hist), _ptr(out), _ptr(counts),
+                                                 _stream_handle()))
+
+        full = int(self.lib.mcr_select_full_passes())
+        step(0)
+        for p in range(8):
+            if p == full:
+                step(4)  # COLLECT: candidates of the resolved prefixes (local shard)
+            step(1, p)
+            all_reduce(hist)
+            step(2, p)
+        step(3)
 
     def first_year_rates(self, start, fy_real, n: int, rates) -> None:
         self._check(self.lib.mcr_first_year_rates(self.handle, _ptr(start), _ptr(fy_real), n, _ptr(rates),

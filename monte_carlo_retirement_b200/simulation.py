@@ -177,7 +177,7 @@ class DeviceAggregates:
 
     def to_host(self) -> Dict[str, Any]:
         b = self.batch
-        n, T, R = b.n, b.T, b.R
+        n, T, R = int(getattr(self, "n_override", b.n)), b.T, b.R
         nq, nw, nf = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES), len(FINAL_BALANCE_QUANTILES)
         small = self.small.cpu().numpy()
         cnt = self.counts.cpu().numpy()
@@ -413,6 +413,19 @@ class RetirementMonteCarloSimulator:
         return DeviceBatch(n=n, working_months=wm, T=T, R=R, cols=cols, success=success, ruin=ruin,
                            counters=counters, traj=traj, real=real, wr=wr, shocks=shocks)
 
+    def _staging(self, n: int, dev):
+        """Pinned host staging buffers + a copy stream, cached per batch size."""
+        import torch
+
+        st = getattr(self, "_stage", None)
+        if st is None or st["n"] != n:
+            st = {"n": n, "stream": torch.cuda.Stream(device=dev),
+                  "cols": torch.empty((5, n), dtype=torch.float64, pin_memory=True),
+                  "succ": torch.empty(n, dtype=torch.uint8, pin_memory=True),
+                  "ruin": torch.empty(n, dtype=torch.int32, pin_memory=True)}
+            self._stage = st
+        return st
+
     def _sample_columns(self, n: int) -> List[int]:
         """Columns DataFrame.sample(n=5, axis=1, random_state=main_seed) picks
         (simulation.py:1063-1072): RandomState(seed).choice(n, 5, replace=False)."""
@@ -437,6 +450,19 @@ class RetirementMonteCarloSimulator:
         nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
         sample_cols = self._sample_columns(n)
         k = len(sample_cols)
+
+        # the N x 7 summary columns start their trip to the host (copy engine, side stream) as
+        # soon as the timeline kernel is done, underneath the select kernels
+        main = torch.cuda.current_stream()
+        stage = self._staging(n, dev)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(stage["stream"]):
+            stage["stream"].wait_event(done)
+            stage["cols"].copy_(b.cols, non_blocking=True)
+            stage["succ"].copy_(b.success, non_blocking=True)
+            stage["ruin"].copy_(b.ruin, non_blocking=True)
+
         # one small result block: bands (T*7 *2), WR bands (R*5), samples (k*T *2)
         small = torch.empty(2 * T * nq + R * nw + 2 * k * T, dtype=torch.float64, device=dev)
         o = 0
@@ -451,33 +477,25 @@ class RetirementMonteCarloSimulator:
         ctx.quantiles(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, wr_bands, counts=wr_counts)
         ctx.gather_columns(b.traj, n, T, sample_cols, samples)
         ctx.gather_columns(b.real, n, T, sample_cols, real_samples)
+        host_small = small.cpu()          # synchronises the main stream
+        host_counts = wr_counts.cpu()
+        stage["stream"].synchronize()
+        self.last_d2h_bytes = n * (5 * 8 + 1 + 4) + host_small.numel() * 8 + R * 8
 
-        # device -> host: the 7 summary columns + the small block
-        host_cols = torch.empty((5, n), dtype=torch.float64, pin_memory=True)
-        host_succ = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        host_ruin = torch.empty(n, dtype=torch.int32, pin_memory=True)
-        host_small = torch.empty(small.shape, dtype=torch.float64, pin_memory=True)
-        host_counts = torch.empty(R, dtype=torch.int64, pin_memory=True)
-        host_cols.copy_(b.cols, non_blocking=True)
-        host_succ.copy_(b.success, non_blocking=True)
-        host_ruin.copy_(b.ruin, non_blocking=True)
-        host_small.copy_(small, non_blocking=True)
-        host_counts.copy_(wr_counts, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        self.last_d2h_bytes = (host_cols.numel() * 8 + n + 4 * n + host_small.numel() * 8 + R * 8)
-
-        c = host_cols.numpy()
-        ruin = host_ruin.numpy()
-        years_to_ruin = np.where(ruin < 0, np.nan, ruin.astype(np.float64) / MONTHS_PER_YEAR)
+        c = stage["cols"].numpy().copy()  # the staging buffers are reused by the next call
+        ruin = stage["ruin"].numpy()
+        years_to_ruin = ruin.astype(np.float64)
+        years_to_ruin /= MONTHS_PER_YEAR
+        years_to_ruin[ruin < 0] = np.nan
         summary_df = pd.DataFrame({
             "Start Balance": c[0],
             "Final Balance": c[1],
-            "Success": host_succ.numpy().astype(bool),
+            "Success": stage["succ"].numpy().astype(bool),
             "YearsToRuin": years_to_ruin,
             "First Year Gross Withdrawal": c[2],
             "First Year Real Gross Withdrawal": c[3],
             "Inflation At Retirement": c[4],
-        })
+        }, copy=False)
         s = host_small.numpy()
         o = 0
         traj_pct = pd.DataFrame(s[o:o + T * nq].reshape(T, nq).copy(), columns=TRAJECTORY_QUANTILES); o += T * nq
