@@ -291,6 +291,7 @@ int mcr_replay(mcr_ctx* ctx, const double* shocks_dev, int64_t shocks_ld, int32_
   fill_windows(ctx, working_months, A.window);
   A.shocks = shocks_dev;
   A.shocks_ld = shocks_ld;
+  A.n_months = n_months;
   A.out = *out;
   MCR_CUDA(ctx, pick(flags).timeline(ctx->dev, A, true, (cudaStream_t)stream));
   ctx->launches += 1;
@@ -329,6 +330,7 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
   fill_windows(ctx, working_months, A.window);
   A.shocks = d_sh;
   A.shocks_ld = 1;  // [(m*3 + c) * 1 + 0] == row-major (n_months, 3)
+  A.n_months = n_months;
   A.out.start_balance = d_sc + 0;
   A.out.final_balance = d_sc + 1;
   A.out.first_year_gross = d_sc + 2;

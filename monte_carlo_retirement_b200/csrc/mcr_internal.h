@@ -17,6 +17,7 @@ struct TimelineArgs {
   int32_t window[2 * MCR_MAX_STREAMS];   // per live stream: first paying retirement month, end (exclusive)
   const double* shocks;           // replay only
   int64_t shocks_ld;
+  int32_t n_months;               // replay only: rows of the shock matrix
   mcr_outputs out;
 };
 

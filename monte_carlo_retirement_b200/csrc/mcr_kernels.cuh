@@ -57,7 +57,7 @@ __device__ __forceinline__ void emit_outputs(const mcr_outputs& out, int64_t i, 
   }
 }
 
-template <bool FAST, bool REPLAY>
+template <bool FAST, bool REPLAY, class C>
 __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_timeline(const __grid_constant__ DevParams P,
                                                      const __grid_constant__ TimelineArgs A) {
   extern __shared__ uint32_t s_obs[];
@@ -72,13 +72,13 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_timeline(const __gri
     sink.real = A.out.real_trajectory ? A.out.real_trajectory + i : nullptr;
     sink.wrp = A.out.wr_trajectory ? A.out.wr_trajectory + i : nullptr;
     if constexpr (REPLAY) {
-      ReplayShock sh{A.shocks + i, A.shocks_ld};
-      run_timeline<FAST>(P, A.wm, A.window, sh, sink, o, years_observed);
+      ReplayShock sh{A.shocks + i, A.shocks_ld, A.n_months};
+      run_timeline<FAST, C>(P, A.wm, A.window, sh, sink, o, years_observed);
     } else {
       const uint64_t gp = (uint64_t)(A.first_path + i);
       PhiloxShock<FAST> sh{A.k0, A.k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
                            P.rho_f, P.rho_c_f, P.rho, P.rho_c};
-      run_timeline<FAST>(P, A.wm, A.window, sh, sink, o, years_observed);
+      run_timeline<FAST, C>(P, A.wm, A.window, sh, sink, o, years_observed);
     }
   }
   emit_outputs(A.out, i, valid, o, years_observed, P.R, s_obs);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_timeline(const __gri
 // Batched search: blockIdx.y = candidate (host orders them longest first), blockIdx.x = tile
 // of 128 paths. All 32 lanes of a warp share the candidate, so they fail at similar months;
 // no series, no per-path outputs: only the success count (and executed months) per candidate.
-template <bool FAST>
+template <bool FAST, class C>
 __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_constant__ DevParams P,
                                                    const __grid_constant__ SearchArgs A) {
   const int c = blockIdx.y;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_
     const uint64_t gp = (uint64_t)(A.first_path + i);
     PhiloxShock<FAST> sh{A.k0, A.k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
                          P.rho_f, P.rho_c_f, P.rho, P.rho_c};
-    run_timeline<FAST>(P, A.wm[c], A.window + (size_t)c * 2 * MCR_MAX_STREAMS, sh, sink, o, years_observed);
+    run_timeline<FAST, C>(P, A.wm[c], A.window + (size_t)c * 2 * MCR_MAX_STREAMS, sh, sink, o, years_observed);
   }
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ok = __ballot_sync(0xffffffffu, valid && o.success);
@@ -148,19 +148,40 @@ __global__ void k_helper(const __grid_constant__ DevParams P, int which, double 
 }
 
 // ---- launchers ---------------------------------------------------------------------------
+// which compile-time specialisation matches this scenario (0 generic, 1 both taxed, 2 no tax)
+static int pick_cfg(const DevParams& P) {
+  if (P.taxed1 && P.taxed2 && !P.annual_any) return 1;
+  if (!P.taxed1 && !P.taxed2 && !P.annual_any) return 2;
+  return 0;
+}
+
+template <class C>
+static void launch_timeline_cfg(const DevParams& P, const TimelineArgs& A, bool replay, unsigned grid, size_t smem,
+                                cudaStream_t st) {
+  if (replay)
+    k_timeline<MCR_FAST != 0, true, C><<<grid, kBlock, smem, st>>>(P, A);
+  else
+    k_timeline<MCR_FAST != 0, false, C><<<grid, kBlock, smem, st>>>(P, A);
+}
+
 static cudaError_t launch_timeline(const DevParams& P, const TimelineArgs& A, bool replay, cudaStream_t st) {
   const unsigned grid = (unsigned)((A.n_paths + kBlock - 1) / kBlock);
   const size_t smem = A.out.wr_obs_count ? sizeof(uint32_t) * (size_t)(P.R + 1) : 0;
-  if (replay)
-    k_timeline<MCR_FAST != 0, true><<<grid, kBlock, smem, st>>>(P, A);
-  else
-    k_timeline<MCR_FAST != 0, false><<<grid, kBlock, smem, st>>>(P, A);
+  switch (pick_cfg(P)) {
+    case 1: launch_timeline_cfg<CfgBothTaxed>(P, A, replay, grid, smem, st); break;
+    case 2: launch_timeline_cfg<CfgNoTax>(P, A, replay, grid, smem, st); break;
+    default: launch_timeline_cfg<CfgGeneric>(P, A, replay, grid, smem, st); break;
+  }
   return cudaGetLastError();
 }
 
 static cudaError_t launch_search(const DevParams& P, const SearchArgs& A, cudaStream_t st) {
   dim3 grid((unsigned)((A.n_paths + kBlock - 1) / kBlock), (unsigned)A.n_candidates);
-  k_search<MCR_FAST != 0><<<grid, kBlock, 0, st>>>(P, A);
+  switch (pick_cfg(P)) {
+    case 1: k_search<MCR_FAST != 0, CfgBothTaxed><<<grid, kBlock, 0, st>>>(P, A); break;
+    case 2: k_search<MCR_FAST != 0, CfgNoTax><<<grid, kBlock, 0, st>>>(P, A); break;
+    default: k_search<MCR_FAST != 0, CfgGeneric><<<grid, kBlock, 0, st>>>(P, A); break;
+  }
   return cudaGetLastError();
 }
 

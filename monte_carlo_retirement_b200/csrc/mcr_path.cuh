@@ -72,6 +72,26 @@ struct PathOut {
   uint32_t executed;   // months stepped (shock rows consumed)
 };
 
+// Compile-time view of the scenario's tax switches. The switches are warp-uniform, but as run-time
+// branches they cut the month into many small basic blocks and keep the two withdrawals (and
+// other independent chains) from being interleaved by the scheduler; the launcher therefore
+// picks a specialisation when the scenario matches one (-1 = read the flag at run time).
+template <int TAXED1, int TAXED2, int ANNUAL>
+struct Cfg {
+  static __device__ __forceinline__ bool taxed1(const DevParams& P) {
+    if constexpr (TAXED1 < 0) return P.taxed1 != 0; else return TAXED1 != 0;
+  }
+  static __device__ __forceinline__ bool taxed2(const DevParams& P) {
+    if constexpr (TAXED2 < 0) return P.taxed2 != 0; else return TAXED2 != 0;
+  }
+  static __device__ __forceinline__ bool annual(const DevParams& P) {
+    if constexpr (ANNUAL < 0) return P.annual_any != 0; else return ANNUAL != 0;
+  }
+};
+using CfgGeneric = Cfg<-1, -1, -1>;
+using CfgBothTaxed = Cfg<1, 1, 0>;   // both assets on the realized-gains system with a positive rate, no annual tax
+using CfgNoTax = Cfg<0, 0, 0>;       // no realized-gains tax bites and no annual tax
+
 // CPython max(a, b) / min(a, b): first argument wins ties and NaN compares. Written as
 // setp + selp so the compiler cannot canonicalise them into fmax/fmin, whose NaN-correct SASS
 // expansion is 6 instructions instead of DSETP + 2 SEL.
@@ -110,6 +130,40 @@ struct Math {
     } else {
       return 1.0 / b;
     }
+  }
+  // a / b: IEEE in the strict build; a * rcp(b) (<= 2 ulp, no slow-path branch) in the fast one
+  static __device__ __forceinline__ double div(double a, double b) {
+    if constexpr (FAST) return a * rcp(b);
+    else return a / b;
+  }
+  static __device__ __forceinline__ double poly_exp(double x) {
+    double p = kExpC[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, x, kExpC[i]);
+    p = fma(p, x, 1.0);
+    return fma(p, x, 1.0);
+  }
+  // the three monthly gross factors exp(mu/12 + sigma/sqrt(12)*z) — simulation.py:468-474,522-530.
+  // Fast build: ONE combined range test (integer compare on the high words), then three
+  // interleaved Horner chains in a single basic block.
+  static __device__ __forceinline__ void factors(const DevParams& P, double ze, double zi, double zp, double& G1,
+                                                 double& GI, double& GP) {
+    const double x1 = P.mu1 + P.sg1 * ze;  // strict: two roundings (no FMA); fast: one DFMA
+    const double xi = P.muI + P.sgI * zi;
+    const double xp = P.muP + P.sgP * zp;
+    if constexpr (FAST) {
+      const int h1 = __double2hiint(x1) & 0x7fffffff, hi = __double2hiint(xi) & 0x7fffffff,
+                hp = __double2hiint(xp) & 0x7fffffff;
+      if (__builtin_expect(max(h1, max(hi, hp)) < 0x3FD5C28F, 1)) {  // all |x| < 0.34
+        G1 = poly_exp(x1);
+        GI = poly_exp(xi);
+        GP = poly_exp(xp);
+        return;
+      }
+    }
+    G1 = exp(x1);
+    GI = exp(xi);
+    GP = exp(xp);
   }
   // monthly gross factor exp(mu + sg * z) — simulation.py:468-474
   static __device__ __forceinline__ double gross(double mu, double sg, double z) {
@@ -153,16 +207,10 @@ __device__ __forceinline__ double net_liq(double bal, double cb, bool taxed, dou
 }
 
 // _calculate_withdrawal_and_update — simulation.py:201-254
+// main path (the early-out of :218-219 is tested by the callers)
 template <bool FAST, bool FULL>
-__device__ __forceinline__ void withdraw(double& bal, double& cb, double target, bool taxed, double rate,
-                                         double& gross, double& net) {
-  if (__builtin_expect(bal <= kEps || target <= 0, 0)) {  // :218-219
-    bal = pmax(0.0, bal);
-    cb = pmax(0.0, cb);
-    gross = 0.0;
-    net = 0.0;
-    return;
-  }
+__device__ __forceinline__ void withdraw_main(double& bal, double& cb, double target, bool taxed, double rate,
+                                              double& gross, double& net) {
   if (!taxed && !FULL) {
     // effective tax fraction 0 -> net_fraction == 1.0, target / 1.0 == target, tax_paid == 0.
     gross = pmin(target, bal);
@@ -198,14 +246,50 @@ __device__ __forceinline__ void withdraw(double& bal, double& cb, double target,
   cb = ncb;
 }
 
+__device__ __forceinline__ bool withdraw_skips(double bal, double target) { return bal <= kEps || target <= 0; }
+
+template <bool FAST, bool FULL>
+__device__ __forceinline__ void withdraw(double& bal, double& cb, double target, bool taxed, double rate,
+                                         double& gross, double& net) {
+  if (__builtin_expect(withdraw_skips(bal, target), 0)) {  // :218-219
+    bal = pmax(0.0, bal);
+    cb = pmax(0.0, cb);
+    gross = 0.0;
+    net = 0.0;
+    return;
+  }
+  withdraw_main<FAST, FULL>(bal, cb, target, taxed, rate, gross, net);
+}
+
+// Both monthly withdrawals with ONE combined early-out test, so the two dependent chains sit in
+// one basic block and interleave (simulation.py:757-777).
+template <bool FAST, class C>
+__device__ __forceinline__ void withdraw_pair(const DevParams& P, double& b1, double& cb1, double t1, double& b2,
+                                              double& cb2, double t2, double& gw1, double& nw1, double& gw2,
+                                              double& nw2) {
+  if (__builtin_expect(!(withdraw_skips(b1, t1) || withdraw_skips(b2, t2)), 1)) {
+    withdraw_main<FAST, false>(b1, cb1, t1, C::taxed1(P), P.rate1, gw1, nw1);
+    withdraw_main<FAST, false>(b2, cb2, t2, C::taxed2(P), P.rate2, gw2, nw2);
+  } else {
+    withdraw<FAST, false>(b1, cb1, t1, C::taxed1(P), P.rate1, gw1, nw1);
+    withdraw<FAST, false>(b2, cb2, t2, C::taxed2(P), P.rate2, gw2, nw2);
+  }
+}
+
 // _rebalance_portfolio — simulation.py:274-359. The sell-asset-1 / sell-asset-2 branches are
 // folded into one straight-line body by selecting the roles (the direction differs per lane,
 // the flags do not), so a warp never executes both.
-template <bool FAST, bool FULL>
-__device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
+// :290-296 — nothing to do when the portfolio is empty or already on target
+__device__ __forceinline__ bool rebalance_skips(const DevParams& P, double b1, double b2) {
+  const double total = b1 + b2;
+  const double drift1 = b1 - total * P.a1;
+  return total <= kEps || fabs(drift1) <= kEps;
+}
+
+template <bool FAST, bool FULL, class C = CfgGeneric>
+__device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
   const double total = b1 + b2;
   const double drift1 = b1 - total * P.a1;                // :293-294
-  if (__builtin_expect(total <= kEps || fabs(drift1) <= kEps, 0)) return;   // :290-291, :295-296
   const bool sell1 = drift1 > 0;
   const double drift2 = b2 - total * P.a2;                // :328 (recomputed, not -drift1)
   const double bs = sell1 ? b1 : b2;
@@ -213,7 +297,7 @@ __device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double
   const double drift = sell1 ? drift1 : drift2;
   // the rebalance consults only the `use` flag (:302-306); use && rate == 0 gives tpd == 0.0
   // exactly, so `taxed` decides the arithmetic in both cases.
-  if (!P.taxed1 && !P.taxed2 && !FULL) {
+  if (!C::taxed1(P) && !C::taxed2(P) && !FULL) {
     const double sale = pmin(bs, drift);   // denominator == max(eps, 1.0 - a*0.0) == 1.0; tax_paid == 0.0
     double nbs = bs - sale;                // identity: max(0, .), sale <= bs
     double nbo = bo + sale;
@@ -255,17 +339,23 @@ __device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double
   cb2 = sell1 ? ncbo : ncbs;
 }
 
+template <bool FAST, bool FULL, class C = CfgGeneric>
+__device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
+  if (__builtin_expect(rebalance_skips(P, b1, b2), 0)) return;
+  rebalance_main<FAST, FULL, C>(P, b1, cb1, b2, cb2);
+}
+
 // _apply_annual_gain_taxes — simulation.py:361-450. Returns tax_failed.
-template <bool FAST, bool FULL>
+template <bool FAST, bool FULL, class C = CfgGeneric>
 __device__ __forceinline__ bool annual_tax(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2,
                                         double g1, double g2) {
   bool failed = false;
-  if (P.annual_any) {
+  if (C::annual(P)) {
     const double due1 = !P.use1 ? pmax(0.0, g1) * P.ann1 : 0.0;   // :380-384
     const double due2 = !P.use2 ? pmax(0.0, g2) * P.ann2 : 0.0;   // :385-389
     const double due = due1 + due2;
-    const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);      // :392-403
-    const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
+    const double cap1 = net_liq(b1, cb1, C::taxed1(P), P.rate1);  // :392-403
+    const double cap2 = net_liq(b2, cb2, C::taxed2(P), P.rate2);
     const double cap = cap1 + cap2;
     const double pay = pmin(due, cap);                            // :405
     failed = pay < due - kEps;                                    // :406
@@ -273,14 +363,14 @@ __device__ __forceinline__ bool annual_tax(const DevParams& P, double& b1, doubl
       const double share1 = cap1 / cap;
       const double share2 = 1.0 - share1;
       double gw, n1, n2;
-      withdraw<FAST, FULL>(b1, cb1, pay * share1, P.taxed1, P.rate1, gw, n1);
-      withdraw<FAST, FULL>(b2, cb2, pay * share2, P.taxed2, P.rate2, gw, n2);
+      withdraw<FAST, FULL>(b1, cb1, pay * share1, C::taxed1(P), P.rate1, gw, n1);
+      withdraw<FAST, FULL>(b2, cb2, pay * share2, C::taxed2(P), P.rate2, gw, n2);
       if (n1 + n2 < due - kEps) failed = true;
     }
   }
   // else: no asset can owe annual tax -> due == 0.0, pay == min(0.0, cap) == 0.0, nothing is
   // sold and tax_failed is False; only the trailing rebalance of :432-442 runs.
-  rebalance<FAST, FULL>(P, b1, cb1, b2, cb2);                     // :432-442
+  rebalance<FAST, FULL, C>(P, b1, cb1, b2, cb2);                  // :432-442
   return failed;
 }
 
@@ -312,7 +402,16 @@ struct SeriesSink {
 // ---------------------------------------------------------------------------------------------
 // the timeline
 // ---------------------------------------------------------------------------------------------
-template <bool FAST, class Shock, class Sink>
+// Software pipeline: the draws and gross factors of month a+1 are computed while month a is
+// being stepped. They depend only on (seed, path, a+1), never on the path state, so this is a
+// pure scheduling change: inside month a's basic blocks the compiler now has independent INT
+// (Philox), FP32/MUFU (Box-Muller) and FP64 (three exp polynomials) work to interleave with
+// the long dependent chains of the withdrawals and the rebalance.
+struct Factors {
+  double G1, GI, GP;
+};
+
+template <bool FAST, class C, class Shock, class Sink>
 __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
                                              const int32_t* __restrict__ window, Shock& shock,
                                              Sink& sink, PathOut& o, int& years_observed) {
@@ -328,32 +427,42 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
   int t = 0;
   sink.point(t++, P.B0, 1.0);                                // :490-492
 
+  Factors nxt;  // factors of the next month to be stepped (absolute month 0 first)
+  {
+    double ze, zi, zp;
+    shock.next(ze, zi, zp);
+    Math<FAST>::factors(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+  }
+
   // ---- accumulation — :513-579
   int moy = 0;  // (m-1) % 12
   for (int m = 1; m <= wm; ++m) {
     if (moy == 0 && m > 1 && P.growth_on) contrib *= P.growth1p;   // :514-517
+    const Factors cur = nxt;
     double ze, zi, zp;
-    shock.next(ze, zi, zp);
+    shock.next(ze, zi, zp);                                        // draws of the FOLLOWING month
     ++executed;
-    const double G1 = Math<FAST>::gross(P.mu1, P.sg1, ze);
-    const double GI = Math<FAST>::gross(P.muI, P.sgI, zi);
-    const double GP = Math<FAST>::gross(P.muP, P.sgP, zp);
-    const double G2 = GI * GP;                                     // :532
-    if (P.annual_any) {
-      g1 += b1 * (G1 - 1.0);                                       // :534-535
+    const double G2 = cur.GI * cur.GP;                             // :532
+    if (C::annual(P)) {
+      g1 += b1 * (cur.G1 - 1.0);                                   // :534-535
       g2 += b2 * (G2 - 1.0);
     }
-    b1 *= G1;
+    b1 *= cur.G1;
     b2 *= G2;
-    level *= GI;
+    level *= cur.GI;
     const double k1 = contrib * P.a1;                              // :540-547
     const double k2 = contrib - k1;
     b1 += k1; cb1 += k1;
     b2 += k2; cb2 += k2;
-    rebalance<FAST, false>(P, b1, cb1, b2, cb2);                   // :549-553
+    if (__builtin_expect(!rebalance_skips(P, b1, b2), 1)) {        // :549-553
+      rebalance_main<FAST, false, C>(P, b1, cb1, b2, cb2);
+      Math<FAST>::factors(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+    } else {
+      Math<FAST>::factors(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+    }
     if (++moy == kMPY) {                                           // m % 12 == 0 — :557-579
       moy = 0;
-      if (annual_tax<FAST, false>(P, b1, cb1, b2, cb2, g1, g2)) pre_fail = true;
+      if (annual_tax<FAST, false, C>(P, b1, cb1, b2, cb2, g1, g2)) pre_fail = true;
       sink.point(t++, b1 + b2, level);
       g1 = 0.0; g2 = 0.0;
     }
@@ -395,50 +504,54 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
         if (lk && !was) { lockn[k] = lv; lockn_mask |= 1u << k; }
       }
       const double need = pmax(0.0, need_nominal - income);        // :679-682
-      if (b1 + b2 <= kEps && need > kEps) { failed = true; break; }  // :684-690
+      const bool wants = need > kEps;
+      if (__builtin_expect(b1 + b2 <= kEps && wants, 0)) { failed = true; break; }  // :684-690
 
+      const Factors cur = nxt;
       double ze, zi, zp;
-      shock.next(ze, zi, zp);
+      shock.next(ze, zi, zp);                                      // draws of the FOLLOWING month
       ++executed;
-      const double G1 = Math<FAST>::gross(P.mu1, P.sg1, ze);
-      const double GI = Math<FAST>::gross(P.muI, P.sgI, zi);
-      const double GP = Math<FAST>::gross(P.muP, P.sgP, zp);
-      const double G2 = GI * GP;
-      if (P.annual_any) {
-        g1 += b1 * (G1 - 1.0);                                     // :706-711
+      const double G2 = cur.GI * cur.GP;
+      if (C::annual(P)) {
+        g1 += b1 * (cur.G1 - 1.0);                                 // :706-711
         g2 += b2 * (G2 - 1.0);
       }
-      b1 *= G1;
+      b1 *= cur.G1;
       b2 *= G2;
-      level *= GI;
-      if (b1 + b2 <= kEps && need > kEps) {                        // :715-724
+      level *= cur.GI;
+      if (__builtin_expect(b1 + b2 <= kEps && wants, 0)) {         // :715-724
         b1 = pmax(0.0, b1);
         b2 = pmax(0.0, b2);
         failed = true;
         break;
       }
-      const double cap1 = net_liq(b1, cb1, P.taxed1, P.rate1);     // :726-737
-      const double cap2 = net_liq(b2, cb2, P.taxed2, P.rate2);
+      const double cap1 = net_liq(b1, cb1, C::taxed1(P), P.rate1); // :726-737
+      const double cap2 = net_liq(b2, cb2, C::taxed2(P), P.rate2);
       const double cap = cap1 + cap2;
       const double target = pmin(need, cap);   // :739-742 identity: max(0, .), need >= +0.0 and cap >= +0.0
-      if (need > kEps && target < need - kEps) failed = true;      // :743-748
-      const double w1 = cap > kEps ? cap1 / cap : P.a1;            // :750-755
+      const double need_lo = need - kEps;
+      if (wants && target < need_lo) failed = true;                // :743-748
+      const double w1 = cap > kEps ? Math<FAST>::div(cap1, cap) : P.a1;   // :750-755
       const double w2 = 1.0 - w1;
       double gw1, nw1, gw2, nw2;
-      withdraw<FAST, false>(b1, cb1, target * w1, P.taxed1, P.rate1, gw1, nw1);   // :757-777
-      withdraw<FAST, false>(b2, cb2, target * w2, P.taxed2, P.rate2, gw2, nw2);
+      withdraw_pair<FAST, C>(P, b1, cb1, target * w1, b2, cb2, target * w2, gw1, nw1, gw2, nw2);  // :757-777
       yr_g1 += gw1;
       yr_g2 += gw2;
-      yr_real += (gw1 + gw2) * level_ret / pmax(level0, kEps);     // :778-782
-      if (need > kEps && nw1 + nw2 < need - kEps) failed = true;   // :784-790
-      rebalance<FAST, false>(P, b1, cb1, b2, cb2);                 // :792-796
+      yr_real += Math<FAST>::div((gw1 + gw2) * level_ret, pmax(level0, kEps));   // :778-782
+      if (wants && nw1 + nw2 < need_lo) failed = true;             // :784-790
+      if (__builtin_expect(!rebalance_skips(P, b1, b2), 1)) {      // :792-796
+        rebalance_main<FAST, false, C>(P, b1, cb1, b2, cb2);
+        Math<FAST>::factors(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+      } else {
+        Math<FAST>::factors(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+      }
       if (++tax_moy == kMPY) tax_moy = 0;
       if (!failed && tax_moy == 0) {                               // :798-822
-        const bool tf = annual_tax<FAST, false>(P, b1, cb1, b2, cb2, g1, g2);
+        const bool tf = annual_tax<FAST, false, C>(P, b1, cb1, b2, cb2, g1, g2);
         g1 = 0.0; g2 = 0.0;
         if (tf) failed = true;
       }
-      if (failed) { ruin = r + 1; break; }                         // :824-828
+      if (__builtin_expect(failed, 0)) { ruin = r + 1; break; }    // :824-828
     }
     const double yr_gross = yr_g1 + yr_g2;
     if (failed) {                                                  // :842-857
@@ -458,7 +571,7 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
 
   // ---- final partial tax period — :873-898
   if (ok && tax_moy != 0) {
-    if (annual_tax<FAST, false>(P, b1, cb1, b2, cb2, g1, g2)) { ok = false; ruin = R * kMPY; }
+    if (annual_tax<FAST, false, C>(P, b1, cb1, b2, cb2, g1, g2)) { ok = false; ruin = R * kMPY; }
     sink.point(t - 1, b1 + b2, level);   // overwrites the last yearly sample
   }
 

@@ -64,11 +64,17 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 struct ReplayShock {
   const double* p;  // shocks_dev + path
   int64_t ld;
+  int32_t left;     // rows not yet consumed (the timeline prefetches one month ahead)
   __device__ __forceinline__ void next(double& ze, double& zi, double& zp) {
-    ze = __ldcs(p);
-    zi = __ldcs(p + ld);
-    zp = __ldcs(p + 2 * ld);
-    p += 3 * ld;
+    if (left > 0) {
+      ze = __ldcs(p);
+      zi = __ldcs(p + ld);
+      zp = __ldcs(p + 2 * ld);
+      p += 3 * ld;
+      --left;
+    } else {
+      ze = zi = zp = 0.0;  // past the end of the matrix: the prefetched month is never stepped
+    }
   }
 };
 
