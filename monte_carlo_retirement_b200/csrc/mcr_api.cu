@@ -22,6 +22,7 @@ struct mcr_ctx {
   DevParams dev;
   uint64_t main_seed = 0;
   uint32_t k0 = 0, k1 = 0;
+  PhiloxKeys keys;
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
@@ -231,6 +232,7 @@ int mcr_create(const mcr_params* params, uint64_t main_seed, int device, mcr_ctx
   const uint64_t key = splitmix64(splitmix64(main_seed) ^ 0x6D63725F62323030ull /* "mcr_b200" */);
   ctx->k0 = (uint32_t)key;
   ctx->k1 = (uint32_t)(key >> 32);
+  philox_expand_keys(ctx->k0, ctx->k1, ctx->keys);
   *out_ctx = ctx;
   return MCR_OK;
 }
@@ -262,7 +264,7 @@ int mcr_simulate(mcr_ctx* ctx, int seed_stream, int32_t working_months, int64_t 
   TimelineArgs A;
   std::memset(&A, 0, sizeof(A));
   A.wm = working_months;
-  A.k0 = ctx->k0; A.k1 = ctx->k1; A.seed_stream = (uint32_t)seed_stream;
+  A.keys = ctx->keys; A.seed_stream = (uint32_t)seed_stream;
   A.first_path = first_path; A.n_paths = n_paths;
   fill_windows(ctx, working_months, A.window);
   A.out = *out;
@@ -403,7 +405,7 @@ int mcr_draw_shocks(mcr_ctx* ctx, int seed_stream, int64_t first_path, int64_t n
   if (n_paths == 0 || n_months == 0) return MCR_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
-  MCR_CUDA(ctx, pick(flags).draw(ctx->dev, ctx->k0, ctx->k1, (uint32_t)seed_stream, first_path, n_paths, n_months,
+  MCR_CUDA(ctx, pick(flags).draw(ctx->dev, ctx->keys, (uint32_t)seed_stream, first_path, n_paths, n_months,
                                  shocks_dev, shocks_ld, (cudaStream_t)stream));
   ctx->launches += 1;
   return MCR_OK;
@@ -444,7 +446,7 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
   MCR_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
   SearchArgs A;
   std::memset(&A, 0, sizeof(A));
-  A.k0 = ctx->k0; A.k1 = ctx->k1; A.seed_stream = (uint32_t)seed_stream;
+  A.keys = ctx->keys; A.seed_stream = (uint32_t)seed_stream;
   A.n_candidates = n_candidates;
   A.first_path = first_path; A.n_paths = n_paths;
   A.wm = (const int32_t*)ctx->scratch;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/mcr.h"
+#include "mcr_rng.cuh"
 
 namespace mcr {
 
@@ -12,7 +13,8 @@ struct DevParams;
 
 struct TimelineArgs {
   int32_t wm;
-  uint32_t k0, k1, seed_stream;   // Philox key words + seed stream (counter word 3)
+  uint32_t seed_stream;           // counter word 3
+  PhiloxKeys keys;                // expanded Philox key schedule
   int64_t first_path, n_paths;
   int32_t window[2 * MCR_MAX_STREAMS];   // per live stream: first paying retirement month, end (exclusive)
   const double* shocks;           // replay only
@@ -22,7 +24,8 @@ struct TimelineArgs {
 };
 
 struct SearchArgs {
-  uint32_t k0, k1, seed_stream;
+  PhiloxKeys keys;
+  uint32_t seed_stream;
   int32_t n_candidates;
   int64_t first_path, n_paths;
   const int32_t* wm;              // [n_candidates] device, sorted longest first
@@ -35,7 +38,7 @@ struct SearchArgs {
 struct Launchers {
   cudaError_t (*timeline)(const DevParams&, const TimelineArgs&, bool replay, cudaStream_t);
   cudaError_t (*search)(const DevParams&, const SearchArgs&, cudaStream_t);
-  cudaError_t (*draw)(const DevParams&, uint32_t k0, uint32_t k1, uint32_t seed_stream, int64_t first_path,
+  cudaError_t (*draw)(const DevParams&, const PhiloxKeys& keys, uint32_t seed_stream, int64_t first_path,
                       int64_t n_paths, int32_t n_months, double* shocks, int64_t ld, cudaStream_t);
   cudaError_t (*helper)(const DevParams&, int which, double a, double b, double c, double d, int use_tax,
                         double rate, double* out, cudaStream_t);

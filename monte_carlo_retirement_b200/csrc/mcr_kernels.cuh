@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_timeline(const __gri
       run_timeline<FAST, C>(P, A.wm, A.window, sh, sink, o, years_observed);
     } else {
       const uint64_t gp = (uint64_t)(A.first_path + i);
-      PhiloxShock<FAST> sh{A.k0, A.k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
+      PhiloxShock<FAST> sh{A.keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
                            P.rho_f, P.rho_c_f, P.rho, P.rho_c};
       run_timeline<FAST, C>(P, A.wm, A.window, sh, sink, o, years_observed);
     }
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_
   if (valid) {
     NullSink sink;
     const uint64_t gp = (uint64_t)(A.first_path + i);
-    PhiloxShock<FAST> sh{A.k0, A.k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
+    PhiloxShock<FAST> sh{A.keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
                          P.rho_f, P.rho_c_f, P.rho, P.rho_c};
     run_timeline<FAST, C>(P, A.wm[c], A.window + (size_t)c * 2 * MCR_MAX_STREAMS, sh, sink, o, years_observed);
   }
@@ -114,12 +114,13 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_
 // Native shocks written out in the replay layout — the device analogue of `_draw_shock_path`
 // (simulation.py:452-466); lets the tests replay the Philox draws through the CPU oracle.
 template <bool FAST>
-__global__ void k_draw_shocks(const __grid_constant__ DevParams P, uint32_t k0, uint32_t k1, uint32_t seed_stream,
-                              int64_t first_path, int64_t n_paths, int32_t n_months, double* shocks, int64_t ld) {
+__global__ void k_draw_shocks(const __grid_constant__ DevParams P, const __grid_constant__ PhiloxKeys keys,
+                              uint32_t seed_stream, int64_t first_path, int64_t n_paths, int32_t n_months,
+                              double* shocks, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_paths) return;
   const uint64_t gp = (uint64_t)(first_path + i);
-  PhiloxShock<FAST> sh{k0, k1, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, seed_stream, P.rho_f, P.rho_c_f, P.rho, P.rho_c};
+  PhiloxShock<FAST> sh{keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, seed_stream, P.rho_f, P.rho_c_f, P.rho, P.rho_c};
   for (int m = 0; m < n_months; ++m) {
     double ze, zi, zp;
     sh.next(ze, zi, zp);
@@ -185,10 +186,10 @@ static cudaError_t launch_search(const DevParams& P, const SearchArgs& A, cudaSt
   return cudaGetLastError();
 }
 
-static cudaError_t launch_draw(const DevParams& P, uint32_t k0, uint32_t k1, uint32_t seed_stream, int64_t first_path,
+static cudaError_t launch_draw(const DevParams& P, const PhiloxKeys& keys, uint32_t seed_stream, int64_t first_path,
                                int64_t n_paths, int32_t n_months, double* shocks, int64_t ld, cudaStream_t st) {
   const unsigned grid = (unsigned)((n_paths + 127) / 128);
-  k_draw_shocks<MCR_FAST != 0><<<grid, 128, 0, st>>>(P, k0, k1, seed_stream, first_path, n_paths, n_months, shocks, ld);
+  k_draw_shocks<MCR_FAST != 0><<<grid, 128, 0, st>>>(P, keys, seed_stream, first_path, n_paths, n_months, shocks, ld);
   return cudaGetLastError();
 }
 

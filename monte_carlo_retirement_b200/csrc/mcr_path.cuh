@@ -106,6 +106,24 @@ __device__ __forceinline__ double pmin(double a, double b) {
   return d;
 }
 
+// (a <= c) || (|b| <= c) and (a < c) || (b < c) as two DSETPs + a predicate OR. Written in PTX
+// because the compiler otherwise rewrites the pair into fmin(a, b) < c, whose NaN-correct
+// expansion costs 6 instructions.
+__device__ __forceinline__ bool either_le_abs(double a, double b, double c) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p, q;\n\t.reg .f64 t;\n\tabs.f64 t, %2;\n\tsetp.le.f64 p, %1, %3;\n\t"
+      "setp.le.f64 q, t, %3;\n\tor.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "d"(a), "d"(b), "d"(c));
+  return r != 0;
+}
+__device__ __forceinline__ bool either_lt(double a, double b, double c) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %1, %3;\n\tsetp.lt.f64 q, %2, %3;\n\tor.pred p, p, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "d"(a), "d"(b), "d"(c));
+  return r != 0;
+}
+
 // exp(x) Taylor coefficients 1/13! .. 1/2! — constant-bank operands of the DFMAs (no UMOV pairs)
 static __constant__ double kExpC[12] = {
     1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
@@ -283,7 +301,7 @@ __device__ __forceinline__ void withdraw_pair(const DevParams& P, double& b1, do
 __device__ __forceinline__ bool rebalance_skips(const DevParams& P, double b1, double b2) {
   const double total = b1 + b2;
   const double drift1 = b1 - total * P.a1;
-  return total <= kEps || fabs(drift1) <= kEps;
+  return either_le_abs(total, drift1, kEps);
 }
 
 template <bool FAST, bool FULL, class C = CfgGeneric>
@@ -530,7 +548,6 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
       const double cap = cap1 + cap2;
       const double target = pmin(need, cap);   // :739-742 identity: max(0, .), need >= +0.0 and cap >= +0.0
       const double need_lo = need - kEps;
-      if (wants && target < need_lo) failed = true;                // :743-748
       const double w1 = cap > kEps ? Math<FAST>::div(cap1, cap) : P.a1;   // :750-755
       const double w2 = 1.0 - w1;
       double gw1, nw1, gw2, nw2;
@@ -538,7 +555,7 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
       yr_g1 += gw1;
       yr_g2 += gw2;
       yr_real += Math<FAST>::div((gw1 + gw2) * level_ret, pmax(level0, kEps));   // :778-782
-      if (wants && nw1 + nw2 < need_lo) failed = true;             // :784-790
+      if (wants && either_lt(target, nw1 + nw2, need_lo)) failed = true;   // :743-748 and :784-790
       if (__builtin_expect(!rebalance_skips(P, b1, b2), 1)) {      // :792-796
         rebalance_main<FAST, false, C>(P, b1, cb1, b2, cb2);
         Math<FAST>::factors(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);

@@ -16,21 +16,33 @@
 
 namespace mcr {
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// The key schedule (k + r*W per round) does not depend on the counter: the host expands it once
+// into the launch arguments (PhiloxKeys), so each round is 2 IMAD.WIDE + 2 three-input LOP3 with
+// the round keys as constant-bank operands.
+struct PhiloxKeys {
+  uint32_t rk[20];  // rk[2r], rk[2r+1] = (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85)
+};
+
+__host__ __device__ inline void philox_expand_keys(uint32_t k0, uint32_t k1, PhiloxKeys& K) {
+  for (int r = 0; r < 10; ++r) {
+    K.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+    K.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKeys& K, uint32_t out[4]) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint64_t p0 = (uint64_t)M0 * c0;
     const uint64_t p1 = (uint64_t)M1 * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.rk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.rk[2 * r + 1];
     c1 = (uint32_t)p1;
     c3 = (uint32_t)p0;
     c0 = n0;
     c2 = n2;
-    k0 += W0;
-    k1 += W1;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
@@ -80,12 +92,13 @@ struct ReplayShock {
 
 template <bool FAST>
 struct PhiloxShock {
-  uint32_t k0, k1, p_lo, p_hi, month, strm;
+  const PhiloxKeys& keys;
+  uint32_t p_lo, p_hi, month, strm;
   float rho_f, rho_c_f;
   double rho, rho_c;
   __device__ __forceinline__ void next(double& ze, double& zi, double& zp) {
     uint32_t r[4];
-    philox4x32_10(p_lo, p_hi, month, strm, k0, k1, r);
+    philox4x32_10(p_lo, p_hi, month, strm, keys, r);
     ++month;
     float n0, n1, n2, n3;
     box_muller<FAST>(r[0], r[1], n0, n1);
