@@ -117,11 +117,19 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
 
         ctx = self.native_context
         coll = self.coll
+        import os
+
         n_global = int(num_simulations)
         lo, n = shard_range(n_global, coll.rank, coll.world)
+        series_bytes = 8 * n * (2 * self._trajectory_len(int(working_months)) + self.params_model.retirement_years)
+        free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
+        sweep_t = torch.tensor([int(bool(bands) and (series_bytes > 0.6 * free_bytes
+                                                       or os.environ.get("MCR_SERIES_SWEEP") == "1"))],
+                               dtype=torch.int32, device=self._torch_device())
+        sweep = bool(coll.max_(sweep_t).item())  # every rank takes the same route
         if timeline_events is not None:
             timeline_events[0].record()
-        b = self.run_batch_device(working_months, n, series=bands, first_path=first_path + lo)
+        b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=first_path + lo)
         if timeline_events is not None:
             timeline_events[1].record()
         dev = b.cols.device
@@ -158,10 +166,20 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         if bands:
             band_block = torch.empty(2 * T * nq + R * nw, **f64)
             wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-            ctx.quantiles_distributed(b.traj, n, n, T, TRAJECTORY_QUANTILES, band_block[0:], ar)
-            ctx.quantiles_distributed(b.real, n, n, T, TRAJECTORY_QUANTILES, band_block[T * nq:], ar)
-            ctx.quantiles_distributed(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, band_block[2 * T * nq:], ar,
-                                      counts=wr_counts)
+            if not sweep:
+                ctx.quantiles_distributed(b.traj, n, n, T, TRAJECTORY_QUANTILES, band_block[0:], ar)
+                ctx.quantiles_distributed(b.real, n, n, T, TRAJECTORY_QUANTILES, band_block[T * nq:], ar)
+                ctx.quantiles_distributed(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, band_block[2 * T * nq:], ar,
+                                          counts=wr_counts)
+            else:  # one series at a time (recompute): 1e9-path jobs, see simulation.aggregates_device
+                for which, rows, qs, off in (("traj", T, TRAJECTORY_QUANTILES, 0),
+                                             ("real", T, TRAJECTORY_QUANTILES, T * nq),
+                                             ("wr", R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)):
+                    part = self.run_batch_device(working_months, n, series=which, first_path=first_path + lo)
+                    ctx.quantiles_distributed(getattr(part, which), n, n, rows, qs, band_block[off:], ar,
+                                              counts=wr_counts if which == "wr" else None)
+                    torch.cuda.current_stream().synchronize()
+                    del part
         self._last_batch = b
         from .simulation import DeviceAggregates
 

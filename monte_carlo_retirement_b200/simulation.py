@@ -385,9 +385,12 @@ class RetirementMonteCarloSimulator:
         success = torch.empty(n, dtype=torch.uint8, device=dev)
         ruin = torch.empty(n, dtype=torch.int32, device=dev)
         counters = torch.zeros(2 + 12 * R + 1, dtype=torch.int64, device=dev)  # success, executed, ruin hist
-        traj = torch.empty((T, n), **f64) if series else None
-        real = torch.empty((T, n), **f64) if series else None
-        wr = torch.empty((R, n), **f64) if series else None
+        # series: True (all three), False (none) or one of "traj" / "real" / "wr" (huge batches
+        # whose three series do not fit in HBM together are swept one series at a time)
+        want = {"traj", "real", "wr"} if series is True else (set() if not series else {series})
+        traj = torch.empty((T, n), **f64) if "traj" in want else None
+        real = torch.empty((T, n), **f64) if "real" in want else None
+        wr = torch.empty((R, n), **f64) if "wr" in want else None
         out = native.Outputs()
         out.start_balance = cols[0].data_ptr()
         out.final_balance = cols[1].data_ptr()
@@ -396,9 +399,11 @@ class RetirementMonteCarloSimulator:
         out.inflation_at_ret = cols[4].data_ptr()
         out.success = success.data_ptr()
         out.ruin_month = ruin.data_ptr()
-        if series:
+        if traj is not None:
             out.trajectory = traj.data_ptr()
+        if real is not None:
             out.real_trajectory = real.data_ptr()
+        if wr is not None:
             out.wr_trajectory = wr.data_ptr()
         out.series_ld = n
         out.success_count = counters[0:].data_ptr()
@@ -414,17 +419,17 @@ class RetirementMonteCarloSimulator:
                            counters=counters, traj=traj, real=real, wr=wr, shocks=shocks)
 
     def _staging(self, n: int, dev):
-        """Pinned host staging buffers + a copy stream, cached per batch size."""
+        """Pinned host destination buffers + the copy stream."""
         import torch
 
-        st = getattr(self, "_stage", None)
-        if st is None or st["n"] != n:
-            st = {"n": n, "stream": torch.cuda.Stream(device=dev),
-                  "cols": torch.empty((5, n), dtype=torch.float64, pin_memory=True),
-                  "succ": torch.empty(n, dtype=torch.uint8, pin_memory=True),
-                  "ruin": torch.empty(n, dtype=torch.int32, pin_memory=True)}
-            self._stage = st
-        return st
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        # fresh pinned blocks per call (torch's caching host allocator recycles them once the
+        # previous call's DataFrame is garbage): summary_df is built on these without a copy
+        return {"n": n, "stream": self._copy_stream,
+                "cols": torch.empty((5, n), dtype=torch.float64, pin_memory=True),
+                "succ": torch.empty(n, dtype=torch.uint8, pin_memory=True),
+                "ruin": torch.empty(n, dtype=torch.int32, pin_memory=True)}
 
     def _sample_columns(self, n: int) -> List[int]:
         """Columns DataFrame.sample(n=5, axis=1, random_state=main_seed) picks
@@ -482,7 +487,7 @@ class RetirementMonteCarloSimulator:
         stage["stream"].synchronize()
         self.last_d2h_bytes = n * (5 * 8 + 1 + 4) + host_small.numel() * 8 + R * 8
 
-        c = stage["cols"].numpy().copy()  # the staging buffers are reused by the next call
+        c = stage["cols"].numpy()  # pinned block owned by this call's result (no copy)
         ruin = stage["ruin"].numpy()
         years_to_ruin = ruin.astype(np.float64)
         years_to_ruin /= MONTHS_PER_YEAR
@@ -527,9 +532,13 @@ class RetirementMonteCarloSimulator:
 
         ctx = self.native_context
         n = int(num_simulations)
+        R0 = self.params_model.retirement_years
+        series_bytes = 8 * n * (2 * self._trajectory_len(int(working_months)) + R0)
+        free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
+        sweep = bool(bands) and (series_bytes > 0.6 * free_bytes or os.environ.get("MCR_SERIES_SWEEP") == "1")
         if timeline_events is not None:
             timeline_events[0].record()
-        b = self.run_batch_device(working_months, n, series=bands, first_path=first_path)
+        b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=first_path)
         if timeline_events is not None:
             timeline_events[1].record()
         dev = b.cols.device
@@ -556,9 +565,22 @@ class RetirementMonteCarloSimulator:
         if bands:
             band_block = torch.empty(2 * T * nq + R * nw, **f64)
             wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-            ctx.quantiles(b.traj, n, n, T, TRAJECTORY_QUANTILES, band_block[0:])
-            ctx.quantiles(b.real, n, n, T, TRAJECTORY_QUANTILES, band_block[T * nq:])
-            ctx.quantiles(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, band_block[2 * T * nq:], counts=wr_counts)
+            if not sweep:
+                ctx.quantiles(b.traj, n, n, T, TRAJECTORY_QUANTILES, band_block[0:])
+                ctx.quantiles(b.real, n, n, T, TRAJECTORY_QUANTILES, band_block[T * nq:])
+                ctx.quantiles(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, band_block[2 * T * nq:], counts=wr_counts)
+            else:
+                # the three series do not fit together (e.g. 1.25e8 paths x 71 points = 71 GB each):
+                # recompute the batch once per series — Philox makes every (path, month) draw
+                # reproducible, so this costs kernel time, not memory or precision
+                for which, rows, qs, off in (("traj", T, TRAJECTORY_QUANTILES, 0),
+                                             ("real", T, TRAJECTORY_QUANTILES, T * nq),
+                                             ("wr", R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)):
+                    part = self.run_batch_device(working_months, n, series=which, first_path=first_path)
+                    ctx.quantiles(getattr(part, which), n, n, rows, qs, band_block[off:],
+                                  counts=wr_counts if which == "wr" else None)
+                    torch.cuda.current_stream().synchronize()  # release the series before the next one
+                    del part
         self._last_batch = b
         return DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
                                 wr_counts=wr_counts, rates=rates)

@@ -378,3 +378,27 @@ def test_crn_success_probability_is_monotone_in_working_months():
     assert all(b + 1e-9 >= a for a, b in zip(probs, probs[1:])), probs
     counts = sim.batched_success_counts(list(range(0, 61, 6)), 80).cpu().numpy()
     assert np.allclose(counts / 80 * 100.0, probs)
+
+
+def test_series_sweep_mode_equals_all_at_once(monkeypatch):
+    """Config #5 shape: when the three series do not fit in HBM together they are produced one
+    at a time by recomputing the batch; the bands must be identical."""
+    sim = make_sim(scenarios.SYNTH_C3_VOL)
+    a = sim.run_aggregates(100, 30_000)
+    monkeypatch.setenv("MCR_SERIES_SWEEP", "1")
+    b = sim.run_aggregates(100, 30_000)
+    for k in ("trajectory_bands", "real_trajectory_bands", "withdrawal_rate_bands"):
+        assert np.array_equal(a[k].to_numpy(), b[k].to_numpy(), equal_nan=True), k
+    assert a["withdrawal_rate_counts"] == b["withdrawal_rate_counts"]
+    assert a["success_count"] == b["success_count"]
+
+
+def test_large_batch_aggregate_only_mode():
+    """8e6 paths in one launch without series: counts add up, medians are sane."""
+    sim = make_sim(scenarios.SYNTH_C3)
+    h = sim.run_aggregates(240, 8_000_000, bands=False)
+    assert h["num_simulations"] == 8_000_000
+    assert h["executed_path_months"] <= 8_000_000 * 720
+    assert sum(h["ruin_month_hist"]) == 8_000_000 - h["success_count"]
+    assert sum(h["final_balance_hist_musd_100"]["counts"]) == h["success_count"]
+    assert 99.0 < h["success_probability"] < 100.0
