@@ -140,6 +140,14 @@ int validate_and_derive(const mcr_params& p, DevParams& d, double* live_start_ag
   d.taxed2 = d.use2 && d.rate2 > 0;
   d.growth_on = p.contribution_growth_rate_annual > 0;
   d.annual_any = (!d.use1 && d.ann1 > 0) || (!d.use2 && d.ann2 > 0);
+  {
+    // |mu/12| + sigma/sqrt(12) * z_max for the three factors; Box-Muller on 32-bit uniforms
+    // gives |n| <= sqrt(-2 ln 2^-33) = 6.77, the inflation shock is rho*n0 + rho_c*n1
+    const double zmax = 6.8, zinf = zmax * (std::fabs(d.rho) + d.rho_c);
+    const double b1 = std::fabs(d.mu1) + d.sg1 * zmax, bi = std::fabs(d.muI) + d.sgI * zinf,
+                 bp = std::fabs(d.muP) + d.sgP * zmax;
+    d.exp_small = (b1 < 0.1 && bi < 0.1 && bp < 0.1) ? 1 : 0;
+  }
   d.R = p.retirement_years;
   int live = 0;
   for (int k = 0; k < p.n_streams; ++k) {

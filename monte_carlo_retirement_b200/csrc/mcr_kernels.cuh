@@ -149,10 +149,12 @@ __global__ void k_helper(const __grid_constant__ DevParams P, int which, double 
 }
 
 // ---- launchers ---------------------------------------------------------------------------
-// which compile-time specialisation matches this scenario (0 generic, 1 both taxed, 2 no tax)
-static int pick_cfg(const DevParams& P) {
-  if (P.taxed1 && P.taxed2 && !P.annual_any) return 1;
-  if (!P.taxed1 && !P.taxed2 && !P.annual_any) return 2;
+// which compile-time specialisation matches this scenario (0 generic, 1 both taxed, 2 no tax;
+// +2 when the short exp polynomial is provably enough — native draws of the fast build only)
+static int pick_cfg(const DevParams& P, bool native_draws) {
+  const int small = (MCR_FAST != 0 && native_draws && P.exp_small) ? 2 : 0;
+  if (P.taxed1 && P.taxed2 && !P.annual_any) return 1 + small;
+  if (!P.taxed1 && !P.taxed2 && !P.annual_any) return 2 + small;
   return 0;
 }
 
@@ -168,9 +170,13 @@ static void launch_timeline_cfg(const DevParams& P, const TimelineArgs& A, bool 
 static cudaError_t launch_timeline(const DevParams& P, const TimelineArgs& A, bool replay, cudaStream_t st) {
   const unsigned grid = (unsigned)((A.n_paths + kBlock - 1) / kBlock);
   const size_t smem = A.out.wr_obs_count ? sizeof(uint32_t) * (size_t)(P.R + 1) : 0;
-  switch (pick_cfg(P)) {
+  switch (pick_cfg(P, !replay)) {
     case 1: launch_timeline_cfg<CfgBothTaxed>(P, A, replay, grid, smem, st); break;
     case 2: launch_timeline_cfg<CfgNoTax>(P, A, replay, grid, smem, st); break;
+#if MCR_FAST
+    case 3: k_timeline<true, false, CfgBothTaxedSmall><<<grid, kBlock, smem, st>>>(P, A); break;
+    case 4: k_timeline<true, false, CfgNoTaxSmall><<<grid, kBlock, smem, st>>>(P, A); break;
+#endif
     default: launch_timeline_cfg<CfgGeneric>(P, A, replay, grid, smem, st); break;
   }
   return cudaGetLastError();
@@ -178,9 +184,13 @@ static cudaError_t launch_timeline(const DevParams& P, const TimelineArgs& A, bo
 
 static cudaError_t launch_search(const DevParams& P, const SearchArgs& A, cudaStream_t st) {
   dim3 grid((unsigned)((A.n_paths + kBlock - 1) / kBlock), (unsigned)A.n_candidates);
-  switch (pick_cfg(P)) {
+  switch (pick_cfg(P, true)) {
     case 1: k_search<MCR_FAST != 0, CfgBothTaxed><<<grid, kBlock, 0, st>>>(P, A); break;
     case 2: k_search<MCR_FAST != 0, CfgNoTax><<<grid, kBlock, 0, st>>>(P, A); break;
+#if MCR_FAST
+    case 3: k_search<true, CfgBothTaxedSmall><<<grid, kBlock, 0, st>>>(P, A); break;
+    case 4: k_search<true, CfgNoTaxSmall><<<grid, kBlock, 0, st>>>(P, A); break;
+#endif
     default: k_search<MCR_FAST != 0, CfgGeneric><<<grid, kBlock, 0, st>>>(P, A); break;
   }
   return cudaGetLastError();

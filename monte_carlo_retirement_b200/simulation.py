@@ -251,9 +251,9 @@ class RetirementMonteCarloSimulator:
         if self.rng_mode not in ("philox", "numpy"):
             raise ValueError("rng must be 'philox' or 'numpy'")
         self.strict = bool(int(os.environ.get("MCR_STRICT", "0"))) if strict is None else bool(strict)
-        self.search_policy = (search_policy or os.environ.get("MCR_SEARCH_POLICY", "waves")).lower()
-        if self.search_policy not in ("waves", "grid", "sequential"):
-            raise ValueError("search_policy must be 'waves', 'grid' or 'sequential'")
+        self.search_policy = (search_policy or os.environ.get("MCR_SEARCH_POLICY", "auto")).lower()
+        if self.search_policy not in ("auto", "waves", "probe", "grid", "sequential"):
+            raise ValueError("search_policy must be 'auto', 'waves', 'probe', 'grid' or 'sequential'")
         self._device_index = device
         self._ctx: Optional[native.Context] = None
         self.last_search_stats: Dict[str, Any] = {}
@@ -637,8 +637,14 @@ class RetirementMonteCarloSimulator:
             type(self).run_monte_carlo_simulations is not RetirementMonteCarloSimulator.run_monte_carlo_simulations
             and not getattr(self, "_device_search_ok", False))
         use_device_batches = not patched and self.search_policy != "sequential" and self.rng_mode == "philox"
+        # auto: speculative waves while one candidate cannot fill the GPU (a launch per probe is
+        # then latency-bound), one search launch per probe once a single candidate saturates it
+        policy = self.search_policy
+        if policy == "auto":
+            policy = "waves" if sim_count < 131072 else "probe"
+        speculate = use_device_batches and policy == "waves"
         table: Dict[int, int] = {}  # working_months -> success count (device-evaluated)
-        stats = {"launches": 0, "candidates_evaluated": 0, "policy": self.search_policy if use_device_batches else "sequential"}
+        stats = {"launches": 0, "candidates_evaluated": 0, "policy": policy if use_device_batches else "sequential"}
 
         def prefetch(months: Iterable[int]) -> None:
             if not use_device_batches:
@@ -692,10 +698,8 @@ class RetirementMonteCarloSimulator:
             return result
 
         # ---- phase 1: bracket (simulation.py:1224-1279)
-        if self.search_policy == "grid":
+        if use_device_batches and policy == "grid":
             prefetch(range(start, min(start + 600, max_total_months) + 1))
-        else:
-            prefetch([start])
         step = 12
         current = start
         prob_at_lo = _test(current)
@@ -720,7 +724,7 @@ class RetirementMonteCarloSimulator:
             next_months = min(current + step, max_total_months)
             if next_months <= current:
                 break
-            if use_device_batches and next_months not in table:
+            if speculate and next_months not in table:
                 for w in waves:
                     if next_months in w:
                         prefetch(w)
@@ -748,7 +752,7 @@ class RetirementMonteCarloSimulator:
         # ---- phases 2+3 need every month from a conservative verification start up to hi: the
         # start can only move later once bisection points are known, so one launch covers both.
         margin = min(100.0, 150.0 / math.sqrt(sim_count))
-        if use_device_batches:
+        if speculate:
             tested = sorted(m for m in cache if m <= state["hi"])
             near = next((i for i, m in enumerate(tested) if cache[m] >= target - margin), len(tested) - 1)
             prefetch(range(max(start, tested[max(0, near - 1)]), state["hi"] + 1))

@@ -73,7 +73,7 @@ def _worker(rank, world, port, out_dir):
             return torch.tensor([int(_path_succeeds(idx, c).sum()) for c in candidates], dtype=torch.int64)
 
         RetirementMonteCarloSimulator.batched_success_counts = fake_counts  # stands in for the CUDA launch
-        sim = ShardedSimulator(cfg, collectives=coll)
+        sim = ShardedSimulator(cfg, collectives=coll, search_policy="waves")
         sim._ctx = object()  # never touched: the fake replaces the only native call of the search
         events = []
         months, prob, curve = sim.find_minimum_working_months(verbose=False, progress_callback=events.append)
