@@ -36,44 +36,64 @@ __device__ __forceinline__ double value_of(uint64_t k) {
 }
 
 // Per-row selection state, resident in the context's scratch between the passes of one call.
-// The radix select is split in per-pass kernels (histogram over all CTAs of a row -> global
-// merge -> one small "advance" step) so that (a) a row is scanned by many SMs at once and (b) a
-// multi-GPU caller can all-reduce the merged histograms between the two halves of a pass and
-// obtain exact GLOBAL order statistics without moving any data.
-// Only the first three digits (24 key bits) are resolved by full scans of the row; a fourth scan
-// collects the (few) elements that share a live 24-bit prefix into a per-row candidate list and
-// the last five digits are resolved on that list. Rows whose candidates do not fit (masses of
-// identical values, e.g. zero-padded failed paths) keep scanning the full row.
-// Layout: the merged histograms live in their own contiguous array hist[rows][kMaxTargets][256]
-// (that is the buffer a multi-GPU caller all-reduces), the rest of the state in SelRow[rows].
+//
+// MSD radix select on the order-preserving 64-bit key. A pass = one grid-wide histogram kernel
+// (rows x 16 K-element chunks, every requested quantile of a row resolved in the same scan,
+// merged into hist[row]) + one small "advance" step that walks each target's bucket to the
+// digit holding its rank. Two things keep the number of FULL scans of a row at 3-4:
+//   * adaptive start: pass 0 also reduces the row's min/max key; all keys share the leading
+//     clz(min ^ max) bits, so those are resolved for free and the 8-bit digits of the following
+//     passes start at the first bit that actually discriminates. A constant row is finished
+//     after pass 0; a tightly concentrated row (early accumulation years) is as cheap as a
+//     wide one;
+//   * collect + tail: after three passes a fourth scan gathers the few elements that still
+//     share a target's prefix into a per-row candidate list; one more kernel sorts that list in
+//     shared memory, reads every target off it and interpolates. A bucket that overflows the
+//     list but holds ONE repeated value (zero-padded failed paths) is recognised by its
+//     min == max; only an overflowing bucket of distinct values falls back to scanning the row.
+// The per-pass split also lets a multi-GPU caller all-reduce hist[] between the two halves of
+// a pass and obtain exact GLOBAL order statistics without moving data; that
+// stepwise protocol uses fixed 8-bit digits (adaptive = 0), since min/max would need their own
+// all-reduce.
+// Layout: hist[rows][kMaxTargets][256] u32 is its own contiguous array (the all-reduced
+// buffer); the rest of the state is SelRow[rows] followed by the candidate lists.
 struct SelRow {
-  uint64_t prefix[kMaxTargets];     // per target (rank-sorted): key bits resolved so far
+  uint64_t prefix[kMaxTargets];     // per target (rank-sorted): the `rb` key bits resolved so far
   int64_t rank[kMaxTargets];        // per target: rank inside the current prefix bucket
   uint64_t uprefix[kMaxTargets];    // sorted unique prefixes (groups) of the current pass
+  uint64_t gmin[kMaxTargets];       // per group at collect time: smallest / largest key seen in the bucket
+  uint64_t gmax[kMaxTargets];       //   (equal => the bucket is one repeated value)
   int32_t group[kMaxTargets];       // target -> group
   int32_t slot[kMaxTargets];        // (quantile, lo/hi) -> rank-sorted target slot
-  int32_t n_groups;
-  int32_t n_cand;                   // elements in this row's candidate list
-  int32_t overflow;                 // candidate list overflowed: keep scanning the full row
-  int32_t pad_;
+  uint64_t kmin, kmax;              // row extremes (pass 0, adaptive mode)
   int64_t n_valid;
+  int32_t n_groups;
+  int32_t rb;                       // resolved bits (64 == done)
+  int32_t n_cand;                   // elements in this row's candidate list
+  int32_t overflow;                 // candidate list overflowed
+  int32_t collected;                // candidate list is valid
+  int32_t adaptive;
 };
 
 constexpr int kHistThreads = 256;
 constexpr int kChunk = 16384;       // elements of one row handled by one CTA
 constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
-constexpr int kFullPasses = 3;      // digits resolved by full scans before the collect
+constexpr int kFullPasses = 3;      // passes that scan the rows before the collect
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 
-__global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist) {
+__global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, int adaptive) {
   SelRow& R = rows[blockIdx.x];
   uint32_t* H = hist + (size_t)blockIdx.x * kHistWords;
   for (int k = threadIdx.x; k < kHistWords; k += blockDim.x) H[k] = 0;
-  if (threadIdx.x == 0) { R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; }
+  if (threadIdx.x == 0) {
+    R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
+    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive;
+  }
+  if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
 
 // membership of a key's resolved-bits part among the live prefixes: a 256-entry table on the
-// last resolved digit (the most discriminating one) with chaining, instead of a binary search
+// low byte of the prefix (the most discriminating one) with chaining, instead of a binary search
 struct PrefixTable {
   uint64_t up[kMaxTargets];
   uint8_t head[256];          // group + 1, 0 == none
@@ -103,33 +123,25 @@ __device__ __forceinline__ int lookup(const PrefixTable& T, uint64_t hi) {
   return -1;
 }
 
-// One pass: histogram of digit `pass` (MSB first) inside every live prefix bucket. Passes below
-// kFullPasses scan the row; later passes scan the row's candidate list unless it overflowed.
-__global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restrict__ values, int64_t n, int64_t ld,
-                                                           const uint8_t* __restrict__ mask,
-                                                           const SelRow* __restrict__ rows,
-                                                           uint32_t* __restrict__ hist,
-                                                           const double* __restrict__ cand, int pass) {
-  extern __shared__ uint32_t sh[];  // [n_groups][256]
-  __shared__ PrefixTable T;
-  const SelRow& R = rows[blockIdx.y];
-  const bool from_cand = pass >= kFullPasses && !R.overflow;
-  if (from_cand && blockIdx.x > 0) return;
-  const int ng = R.n_groups;
-  uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
-  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
-  if (pass > 0) build_table(T, R, ng); else __syncthreads();
-  const double* __restrict__ x = from_cand ? cand + (size_t)blockIdx.y * kCandCap : values + (int64_t)blockIdx.y * ld;
-  const uint8_t* __restrict__ m = from_cand ? nullptr : mask;
-  const int shift = 56 - 8 * pass;
-  const int64_t begin = from_cand ? 0 : (int64_t)blockIdx.x * kChunk;
-  const int64_t stop = from_cand ? (int64_t)R.n_cand : (begin + kChunk < n ? begin + kChunk : n);
-  for (int64_t base = begin; base < stop; base += kHistThreads * 4) {
+// group of key k given `rb` resolved bits (-1: not in a live bucket)
+__device__ __forceinline__ int group_of(const PrefixTable& T, uint64_t k, int rb) {
+  return rb == 0 ? 0 : lookup(T, k >> (64 - rb));
+}
+
+// shared-memory histogram of the next digit (width w below the rb resolved bits) over
+// x[begin, stop) by the calling CTA (nthreads wide); optionally the running min/max key
+__device__ __forceinline__ void hist_scan(const double* __restrict__ x, const uint8_t* __restrict__ m, int64_t begin,
+                                          int64_t stop, int nthreads, int rb, int w, const PrefixTable& T, uint32_t* sh,
+                                          uint64_t* kmin, uint64_t* kmax) {
+  const int shift = 64 - rb - w;
+  const uint32_t dmask = (1u << w) - 1u;
+  uint64_t lo = ~0ull, hi = 0ull;
+  for (int64_t base = begin; base < stop; base += (int64_t)nthreads * 4) {
     double v[4];
     bool ok[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {  // 4 independent loads in flight per thread
-      const int64_t e = base + u * kHistThreads + threadIdx.x;
+      const int64_t e = base + (int64_t)u * nthreads + threadIdx.x;
       ok[u] = e < stop && (!m || m[e]);
       v[u] = ok[u] ? __ldcs(x + e) : 0.0;
     }
@@ -138,8 +150,10 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restr
       int id = -1;
       if (ok[u] && v[u] == v[u]) {  // NaN never takes part (pandas skips it)
         const uint64_t k = key_of(v[u]);
-        const int g = pass > 0 ? lookup(T, k >> (shift + 8)) : 0;
-        if (g >= 0) id = g * 256 + (int)((k >> shift) & 255u);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+        const int g = group_of(T, k, rb);
+        if (g >= 0) id = g * 256 + (int)((uint32_t)(k >> shift) & dmask);
       }
       // concentrated data puts whole warps in one bin: one atomic for the warp in that case
       const int id0 = __shfl_sync(0xffffffffu, id, 0);
@@ -150,21 +164,65 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restr
       }
     }
   }
+  if (kmin) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 < lo ? l2 : lo;
+      hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && lo != ~0ull) {
+      atomicMin((unsigned long long*)kmin, (unsigned long long)lo);
+      atomicMax((unsigned long long*)kmax, (unsigned long long)hi);
+    }
+  }
+}
+
+// One pass, first half: histogram of the next digit inside every live prefix bucket. Rows that
+// are finished skip; rows with a valid candidate list scan that list (one CTA).
+__global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restrict__ values, int64_t n, int64_t ld,
+                                                           const uint8_t* __restrict__ mask, SelRow* __restrict__ rows,
+                                                           uint32_t* __restrict__ hist,
+                                                           const double* __restrict__ cand, int pass) {
+  extern __shared__ uint32_t sh[];  // [n_groups][256]
+  __shared__ PrefixTable T;
+  SelRow& R = rows[blockIdx.y];
+  const int rb = R.rb;
+  if (rb >= 64) return;
+  const bool from_cand = R.collected && !R.overflow;
+  if (from_cand && blockIdx.x > 0) return;
+  const int ng = R.n_groups;
+  uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
+  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
+  if (rb > 0) build_table(T, R, ng); else __syncthreads();
+  const double* __restrict__ x = from_cand ? cand + (size_t)blockIdx.y * kCandCap : values + (int64_t)blockIdx.y * ld;
+  const uint8_t* __restrict__ m = from_cand ? nullptr : mask;
+  const int w = 64 - rb < 8 ? 64 - rb : 8;
+  const int64_t begin = from_cand ? 0 : (int64_t)blockIdx.x * kChunk;
+  const int64_t stop = from_cand ? (int64_t)R.n_cand : (begin + kChunk < n ? begin + kChunk : n);
+  const bool want_minmax = pass == 0 && R.adaptive;
+  hist_scan(x, m, begin, stop, kHistThreads, rb, w, T, sh, want_minmax ? &R.kmin : nullptr, &R.kmax);
   __syncthreads();
   for (int k = threadIdx.x; k < ng * 256; k += kHistThreads)
     if (sh[k]) atomicAdd(&H[k], sh[k]);
 }
 
-// After kFullPasses digits: gather the elements that share a live prefix into the row's list.
+// After kFullPasses passes: gather the elements that share a live prefix into the row's list.
 __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __restrict__ values, int64_t n, int64_t ld,
                                                               const uint8_t* __restrict__ mask,
                                                               SelRow* __restrict__ rows, double* __restrict__ cand) {
   __shared__ PrefixTable T;
+  __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
+  __shared__ int s_full;
   SelRow& R = rows[blockIdx.y];
-  build_table(T, R, R.n_groups);
+  const int rb = R.rb;
+  if (rb >= 64 || R.collected) return;
+  const int ng = R.n_groups;
+  if (threadIdx.x < kMaxTargets) { s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull; }
+  if (threadIdx.x == 0) s_full = 0;
+  build_table(T, R, ng);
   const double* __restrict__ x = values + (int64_t)blockIdx.y * ld;
   double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
-  const int shift = 64 - 8 * kFullPasses;
   const int64_t begin = (int64_t)blockIdx.x * kChunk;
   const int64_t stop = begin + kChunk < n ? begin + kChunk : n;
   for (int64_t base = begin; base < stop; base += kHistThreads * 4) {
@@ -178,147 +236,261 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __re
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (ok[u] && v[u] == v[u] && lookup(T, key_of(v[u]) >> shift) >= 0) {
-        const int at = atomicAdd(&R.n_cand, 1);
-        if (at < kCandCap) out[at] = v[u]; else R.overflow = 1;
+      if (ok[u] && v[u] == v[u]) {
+        const uint64_t k = key_of(v[u]);
+        const int g = group_of(T, k, rb);
+        if (g >= 0) {
+          // bucket extremes (shared-memory atomics, merged once per CTA): a bucket of one
+          // repeated value is recognised later by min == max
+          if (k < s_min[g]) atomicMin(&s_min[g], (unsigned long long)k);
+          if (k > s_max[g]) atomicMax(&s_max[g], (unsigned long long)k);
+          if (!s_full) {
+            const int at = atomicAdd(&R.n_cand, 1);
+            if (at < kCandCap) out[at] = v[u]; else s_full = 1;
+          }
+        }
       }
     }
   }
+  __syncthreads();
+  if (threadIdx.x < ng && s_min[threadIdx.x] != ~0ull) {
+    atomicMin((unsigned long long*)&R.gmin[threadIdx.x], s_min[threadIdx.x]);
+    atomicMax((unsigned long long*)&R.gmax[threadIdx.x], s_max[threadIdx.x]);
+  }
+  if (threadIdx.x == 0 && s_full) R.overflow = 1;
 }
 
 __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   SelRow& R = rows[blockIdx.x];
-  if (threadIdx.x == 0 && R.n_cand > kCandCap) { R.n_cand = kCandCap; R.overflow = 1; }
+  if (threadIdx.x == 0 && R.rb < 64 && !R.collected) {
+    if (R.n_cand > kCandCap) { R.n_cand = kCandCap; R.overflow = 1; }
+    R.collected = 1;
+  }
 }
 
-// Second half of a pass (one warp per target + housekeeping): consume the merged histogram.
-__global__ void __launch_bounds__(1024) k_sel_advance(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
-                                                      QuantileSpec spec, int pass) {
-  SelRow& R = rows[blockIdx.x];
-  uint32_t* H = hist + (size_t)blockIdx.x * kHistWords;
+// One pass, second half (one warp per target + housekeeping): consume the merged histogram H
+// of row R. Needs >= 32 * (2 * n_q) threads; ends with H cleared and the next pass's groups set.
+__device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, const QuantileSpec& spec, int pass) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int nq = spec.n_q, nt = 2 * nq;
-  if (pass == 0) {
-    if (warp == 0) {
-      int64_t part = 0;
-      for (int d = lane; d < 256; d += 32) part += H[d];
+  const int rb = R.rb;
+  if (rb < 64) {
+    if (pass == 0) {
+      if (warp == 0) {
+        int64_t part = 0;
+        for (int d = lane; d < 256; d += 32) part += H[d];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) {
-        const int64_t nv = part;
-        R.n_valid = nv;
-        for (int q = 0; q < nq; ++q) {
-          int64_t lo = 0, hi = 0;
-          if (nv > 0) {
-            if (spec.median) {  // np.median: mean of the two middle order statistics
-              lo = (nv - 1) / 2;
-              hi = nv / 2;
-            } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
-              const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
-              if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
-              else if (vi < 0) { lo = hi = 0; }
-              else { lo = (int64_t)floor(vi); hi = lo + 1; }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) {
+          const int64_t nv = part;
+          R.n_valid = nv;
+          for (int q = 0; q < nq; ++q) {
+            int64_t lo = 0, hi = 0;
+            if (nv > 0) {
+              if (spec.median) {  // np.median: mean of the two middle order statistics
+                lo = (nv - 1) / 2;
+                hi = nv / 2;
+              } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
+                const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
+                if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
+                else if (vi < 0) { lo = hi = 0; }
+                else { lo = (int64_t)floor(vi); hi = lo + 1; }
+              }
             }
+            R.rank[2 * q] = lo;
+            R.rank[2 * q + 1] = hi;
           }
-          R.rank[2 * q] = lo;
-          R.rank[2 * q + 1] = hi;
+          // rank-sort the targets (tiny insertion sort) so that prefixes stay sorted in every
+          // pass; for small n the (lo, hi) pairs of different quantiles interleave.
+          int32_t ord[kMaxTargets];
+          for (int t = 0; t < nt; ++t) ord[t] = t;
+          for (int i = 1; i < nt; ++i) {
+            const int32_t o = ord[i];
+            const int64_t r = R.rank[o];
+            int j = i - 1;
+            while (j >= 0 && R.rank[ord[j]] > r) { ord[j + 1] = ord[j]; --j; }
+            ord[j + 1] = o;
+          }
+          int64_t sorted[kMaxTargets];
+          for (int t = 0; t < nt; ++t) sorted[t] = R.rank[ord[t]];
+          for (int t = 0; t < nt; ++t) {
+            R.rank[t] = sorted[t];
+            R.slot[ord[t]] = t;
+            R.prefix[t] = 0;
+            R.group[t] = 0;
+          }
         }
-        // rank-sort the targets (tiny insertion sort) so that prefixes stay sorted in every
-        // pass; for small n the (lo, hi) pairs of different quantiles interleave.
-        int32_t ord[kMaxTargets];
-        for (int t = 0; t < nt; ++t) ord[t] = t;
-        for (int i = 1; i < nt; ++i) {
-          const int32_t o = ord[i];
-          const int64_t r = R.rank[o];
-          int j = i - 1;
-          while (j >= 0 && R.rank[ord[j]] > r) { ord[j + 1] = ord[j]; --j; }
-          ord[j + 1] = o;
+      }
+      __syncthreads();
+    }
+    // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
+    // holding its rank
+    const int w = 64 - rb < 8 ? 64 - rb : 8;
+    if (warp < nt && R.n_valid > 0) {
+      const uint32_t* h = H + R.group[warp] * 256;
+      uint32_t c[8];
+      uint32_t local = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; local += c[k]; }
+      uint32_t incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const int64_t r = R.rank[warp];
+      const int64_t before = (int64_t)incl - local;
+      const bool mine = r >= before && r < (int64_t)incl;
+      const unsigned who = __ballot_sync(0xffffffffu, mine);
+      if (who == 0) {  // rank beyond the bucket (cannot happen for consistent histograms): last bin
+        if (lane == 31) { R.rank[warp] = 0; R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)((1u << w) - 1u); }
+      } else if (lane == __ffs(who) - 1) {
+        int64_t rr = r - before;
+        int k = 0;
+        for (; k < 7; ++k) {
+          if (rr < (int64_t)c[k]) break;
+          rr -= c[k];
         }
-        int64_t sorted[kMaxTargets];
-        for (int t = 0; t < nt; ++t) sorted[t] = R.rank[ord[t]];
-        for (int t = 0; t < nt; ++t) {
-          R.rank[t] = sorted[t];
-          R.slot[ord[t]] = t;
-          R.prefix[t] = 0;
-          R.group[t] = 0;
-        }
+        R.rank[warp] = rr;
+        R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)(lane * 8 + k);
       }
     }
     __syncthreads();
-  }
-  // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
-  // holding its rank
-  if (warp < nt && R.n_valid > 0) {
-    const uint32_t* h = H + R.group[warp] * 256;
-    uint32_t c[8];
-    uint32_t local = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; local += c[k]; }
-    uint32_t incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    const int64_t r = R.rank[warp];
-    const int64_t before = (int64_t)incl - local;
-    const bool mine = r >= before && r < (int64_t)incl;
-    const unsigned who = __ballot_sync(0xffffffffu, mine);
-    if (who == 0) {  // rank beyond the bucket (cannot happen for consistent histograms): last bin
-      if (lane == 31) { R.rank[warp] = 0; R.prefix[warp] = (R.prefix[warp] << 8) | 255ull; }
-    } else if (lane == __ffs(who) - 1) {
-      int64_t rr = r - before;
-      int k = 0;
-      for (; k < 7; ++k) {
-        if (rr < (int64_t)c[k]) break;
-        rr -= c[k];
+    if (tid == 0) {
+      int nrb = rb + w;
+      if (R.n_valid <= 0) nrb = 64;
+      if (pass == 0 && R.adaptive && R.n_valid > 0) {
+        // every key shares the leading clz(kmin ^ kmax) bits: resolve them for free (ranks do
+        // not change: all elements are in every target's bucket)
+        const uint64_t x = R.kmin ^ R.kmax;
+        const int c = x ? __clzll((long long)x) : 64;
+        if (c > nrb) {
+          nrb = c;
+          for (int t = 0; t < nt; ++t) R.prefix[t] = c == 64 ? R.kmin : (R.kmin >> (64 - c));
+        }
       }
-      R.rank[warp] = rr;
-      R.prefix[warp] = (R.prefix[warp] << 8) | (uint64_t)(lane * 8 + k);
+      R.rb = nrb;
+      // groups of the next pass (targets are rank-sorted, so prefixes are sorted)
+      int g = 0;
+      for (int t = 0; t < nt; ++t) {
+        if (t == 0 || R.prefix[t] != R.uprefix[g - 1]) R.uprefix[g++] = R.prefix[t];
+        R.group[t] = g - 1;
+      }
+      R.n_groups = g < 1 ? 1 : g;
     }
-  }
-  __syncthreads();
-  // groups of the next pass (targets are rank-sorted, so prefixes are sorted) + clear histograms
-  if (tid == 0) {
-    int g = 0;
-    for (int t = 0; t < nt; ++t) {
-      if (t == 0 || R.prefix[t] != R.uprefix[g - 1]) R.uprefix[g++] = R.prefix[t];
-      R.group[t] = g - 1;
-    }
-    R.n_groups = g < 1 ? 1 : g;
   }
   for (int k = tid; k < kHistWords; k += blockDim.x) H[k] = 0;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_sel_advance(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
+                                                      QuantileSpec spec, int pass) {
+  advance_row(rows[blockIdx.x], hist + (size_t)blockIdx.x * kHistWords, spec, pass);
+}
+
+// numpy 'linear' interpolation / np.median rule for quantile `k` of a finished row
+__device__ __forceinline__ double finish_value(const SelRow& R, const QuantileSpec& spec, int k) {
+  const int64_t nv = R.n_valid;
+  if (nv <= 0) return CUDART_NAN;
+  const double a = value_of(R.prefix[R.slot[2 * k]]);
+  const double b = value_of(R.prefix[R.slot[2 * k + 1]]);
+  if (spec.median) return (nv & 1) ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+  const double q = spec.q[k];
+  const double vi = __dmul_rn((double)(nv - 1), q);
+  double prev = floor(vi);
+  if (vi >= (double)(nv - 1)) prev = -1.0;  // numpy _get_indexes: both indexes -> last
+  else if (vi < 0) prev = 0.0;
+  const double t = __dsub_rn(vi, prev);     // gamma
+  const double diff = __dsub_rn(b, a);      // _lerp
+  double res = __dadd_rn(a, __dmul_rn(diff, t));
+  if (t >= 0.5) res = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+  return res;
+}
+
+// Single-GPU tail: whatever is left of a row after the collect, in ONE launch, followed by the
+// interpolation. Candidate lists are bitonic-sorted in shared memory and every target is read
+// off the sorted list; an overflowed bucket of one repeated value is resolved by its extremes;
+// an overflowed bucket of distinct values scans the full row here (slow, rare).
+constexpr int kTailThreads = 1024;
+__global__ void __launch_bounds__(kTailThreads) k_sel_tail(const double* __restrict__ values, int64_t n, int64_t ld,
+                                                           const uint8_t* __restrict__ mask, SelRow* __restrict__ rows,
+                                                           const double* __restrict__ cand, QuantileSpec spec,
+                                                           double* __restrict__ out, int64_t* __restrict__ counts) {
+  extern __shared__ uint64_t s_keys[];  // kCandCap keys (64 KB), reused as the histogram on the slow path
+  __shared__ PrefixTable T;
+  __shared__ int need_scan;
+  SelRow& R = rows[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int nt = 2 * spec.n_q;
+  const int rb = R.rb;
+  if (rb < 64 && R.n_valid > 0 && !R.overflow) {
+    const int nc = R.n_cand;
+    int m = 32;
+    while (m < nc) m <<= 1;
+    const double* __restrict__ c = cand + (size_t)blockIdx.x * kCandCap;
+    for (int i = tid; i < m; i += kTailThreads) s_keys[i] = i < nc ? key_of(c[i]) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {          // bitonic sort, ascending
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < m; i += kTailThreads) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint64_t a = s_keys[i], b = s_keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid < nt) {
+      // candidates of this target = keys sharing its resolved prefix; they are contiguous in
+      // the sorted list and its residual rank counts from the first of them
+      const uint64_t lo_key = R.prefix[tid] << (64 - rb);
+      int lo = 0, hi = nc;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_keys[mid] < lo_key) lo = mid + 1; else hi = mid;
+      }
+      const int64_t at = lo + R.rank[tid];
+      R.prefix[tid] = s_keys[at < nc ? at : nc - 1];
+    }
+    __syncthreads();
+  } else if (rb < 64 && R.n_valid > 0) {
+    if (tid == 0) need_scan = 0;
+    __syncthreads();
+    if (tid < nt) {
+      const int g = R.group[tid];
+      if (R.gmin[g] != R.gmax[g]) need_scan = 1;
+    }
+    __syncthreads();
+    if (!need_scan) {
+      if (tid < nt) R.prefix[tid] = R.gmin[R.group[tid]];
+      __syncthreads();
+    } else {
+      uint32_t* sh = (uint32_t*)s_keys;
+      const double* __restrict__ x = values + (int64_t)blockIdx.x * ld;
+      for (int pass = kFullPasses; R.rb < 64; ++pass) {
+        const int cur = R.rb;
+        const int w = 64 - cur < 8 ? 64 - cur : 8;
+        for (int k = tid; k < kHistWords; k += kTailThreads) sh[k] = 0;
+        build_table(T, R, R.n_groups);
+        hist_scan(x, mask, 0, n, kTailThreads, cur, w, T, sh, nullptr, nullptr);
+        __syncthreads();
+        advance_row(R, sh, spec, pass);
+      }
+    }
+  }
+  if (tid < spec.n_q) out[(int64_t)blockIdx.x * spec.n_q + tid] = finish_value(R, spec, tid);
+  if (tid == 0 && counts) counts[blockIdx.x] = R.n_valid;
 }
 
 __global__ void k_sel_finish(const SelRow* __restrict__ rows, QuantileSpec spec, double* __restrict__ out,
                              int64_t* __restrict__ counts) {
   const SelRow& R = rows[blockIdx.x];
-  const int tid = threadIdx.x;
-  const int nq = spec.n_q;
-  if (tid < nq) {
-    const int64_t nv = R.n_valid;
-    double res = CUDART_NAN;
-    if (nv > 0) {
-      const double a = value_of(R.prefix[R.slot[2 * tid]]);
-      const double b = value_of(R.prefix[R.slot[2 * tid + 1]]);
-      if (spec.median) {
-        res = (nv & 1) ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
-      } else {
-        const double q = spec.q[tid];
-        const double vi = __dmul_rn((double)(nv - 1), q);
-        double prev = floor(vi);
-        if (vi >= (double)(nv - 1)) prev = -1.0;  // numpy _get_indexes: both indexes -> last
-        else if (vi < 0) prev = 0.0;
-        const double t = __dsub_rn(vi, prev);     // gamma
-        const double diff = __dsub_rn(b, a);      // _lerp
-        res = __dadd_rn(a, __dmul_rn(diff, t));
-        if (t >= 0.5) res = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
-      }
-    }
-    out[(int64_t)blockIdx.x * nq + tid] = res;
-  }
-  if (tid == 0 && counts) counts[blockIdx.x] = R.n_valid;
+  if (threadIdx.x < spec.n_q) out[(int64_t)blockIdx.x * spec.n_q + threadIdx.x] = finish_value(R, spec, threadIdx.x);
+  if (threadIdx.x == 0 && counts) counts[blockIdx.x] = R.n_valid;
 }
 
 __global__ void k_rates(const double* __restrict__ start, const double* __restrict__ fy_real, int64_t n,
@@ -462,8 +634,8 @@ size_t quantile_state_bytes(int rows) {
 size_t quantile_hist_bytes(int rows) { return sizeof(uint32_t) * kHistWords * (size_t)(rows > 0 ? rows : 1); }
 static double* cand_of(void* state, int rows) { return (double*)((char*)state + sizeof(SelRow) * (size_t)rows); }
 
-cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st) {
-  if (rows > 0) k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist);
+cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive) {
+  if (rows > 0) k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist, adaptive);
   return cudaGetLastError();
 }
 
@@ -472,7 +644,7 @@ cudaError_t launch_sel_hist(const double* values, int64_t n, int64_t ld, int row
   const unsigned chunks = (unsigned)((n + kChunk - 1) / kChunk);
   if (rows <= 0 || chunks == 0) return cudaSuccess;
   const size_t smem = (size_t)kHistWords * sizeof(uint32_t);
-  k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>(values, n, ld, mask, (const SelRow*)state,
+  k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>(values, n, ld, mask, (SelRow*)state,
                                                                        (uint32_t*)hist, cand_of(state, rows), pass);
   return cudaGetLastError();
 }
@@ -504,22 +676,24 @@ cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int ro
                              cudaStream_t st, int* n_launches) {
   *n_launches = 0;
   if (rows <= 0) return cudaSuccess;
-  cudaError_t e = launch_sel_begin(rows, state, hist, st);
+  cudaError_t e = launch_sel_begin(rows, state, hist, st, /*adaptive=*/1);
   ++*n_launches;
-  for (int pass = 0; pass < 8 && e == cudaSuccess; ++pass) {
-    if (pass == kFullPasses) {
-      e = launch_sel_collect(values, n, ld, rows, mask, state, st);
-      *n_launches += 1 + (n > 0);
-      if (e != cudaSuccess) break;
-    }
+  for (int pass = 0; pass < kFullPasses && e == cudaSuccess; ++pass) {
     e = launch_sel_hist(values, n, ld, rows, mask, pass, state, hist, st);
     *n_launches += n > 0;
     if (e == cudaSuccess) e = launch_sel_advance(rows, spec, pass, state, hist, st);
     ++*n_launches;
   }
-  if (e == cudaSuccess) e = launch_sel_finish(rows, spec, state, out, counts, st);
+  if (e == cudaSuccess) e = launch_sel_collect(values, n, ld, rows, mask, state, st);
+  *n_launches += 1 + (n > 0);
+  if (e != cudaSuccess) return e;
+  // one launch for the remaining digits + interpolation (see k_sel_tail)
+  e = cudaFuncSetAttribute(k_sel_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * kCandCap));
+  if (e != cudaSuccess) return e;
+  k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>(values, n, ld, mask, (SelRow*)state,
+                                                                      cand_of(state, rows), spec, out, counts);
   ++*n_launches;
-  return e;
+  return cudaGetLastError();
 }
 
 int select_full_passes() { return kFullPasses; }

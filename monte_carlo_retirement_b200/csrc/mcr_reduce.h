@@ -21,7 +21,7 @@ cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int ro
                              const QuantileSpec& spec, double* out, int64_t* counts, void* state, void* hist,
                              cudaStream_t st, int* n_launches);
 // the same select, one pass at a time (a multi-GPU caller all-reduces `hist` between hist and advance)
-cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st);
+cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive = 0);
 cudaError_t launch_sel_hist(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, int pass,
                             void* state, void* hist, cudaStream_t st);
 cudaError_t launch_sel_collect(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, void* state,
