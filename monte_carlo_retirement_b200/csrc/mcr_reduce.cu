@@ -63,6 +63,8 @@ struct SelRow {
   uint64_t uprefix[kMaxTargets];    // sorted unique prefixes (groups) of the current pass
   uint64_t gmin[kMaxTargets];       // per group at collect time: smallest / largest key seen in the bucket
   uint64_t gmax[kMaxTargets];       //   (equal => the bucket is one repeated value)
+  int64_t bcount[kMaxTargets];      // per target: population of its current bucket
+  int32_t gbig[kMaxTargets];        // per group: bucket too large for the candidate list (not gathered)
   int32_t group[kMaxTargets];       // target -> group
   int32_t slot[kMaxTargets];        // (quantile, lo/hi) -> rank-sorted target slot
   uint64_t kmin, kmax;              // row extremes (pass 0, adaptive mode)
@@ -78,6 +80,7 @@ struct SelRow {
 constexpr int kHistThreads = 256;
 constexpr int kChunk = 16384;       // elements of one row handled by one CTA
 constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
+constexpr int kBigBucket = 2048;    // buckets above this are not gathered (resolved by min == max, else by scanning)
 constexpr int kFullPasses = 3;      // passes that scan the rows before the collect
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 
@@ -214,11 +217,15 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __re
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
   __shared__ int s_full;
+  __shared__ int s_big[kMaxTargets];
   SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
   if (rb >= 64 || R.collected) return;
   const int ng = R.n_groups;
-  if (threadIdx.x < kMaxTargets) { s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull; }
+  if (threadIdx.x < kMaxTargets) {
+    s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull;
+    s_big[threadIdx.x] = threadIdx.x < ng ? R.gbig[threadIdx.x] : 0;
+  }
   if (threadIdx.x == 0) s_full = 0;
   build_table(T, R, ng);
   const double* __restrict__ x = values + (int64_t)blockIdx.y * ld;
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __re
           // repeated value is recognised later by min == max
           if (k < s_min[g]) atomicMin(&s_min[g], (unsigned long long)k);
           if (k > s_max[g]) atomicMax(&s_max[g], (unsigned long long)k);
-          if (!s_full) {
+          if (!s_big[g] && !s_full) {
             const int at = atomicAdd(&R.n_cand, 1);
             if (at < kCandCap) out[at] = v[u]; else s_full = 1;
           }
@@ -264,6 +271,11 @@ __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   SelRow& R = rows[blockIdx.x];
   if (threadIdx.x == 0 && R.rb < 64 && !R.collected) {
     if (R.n_cand > kCandCap) { R.n_cand = kCandCap; R.overflow = 1; }
+    // stepwise (multi-GPU) protocol: later passes histogram the list, so a row with a bucket
+    // that was not gathered keeps scanning the full row instead
+    if (!R.adaptive)
+      for (int g = 0; g < R.n_groups; ++g)
+        if (R.gbig[g]) R.overflow = 1;
     R.collected = 1;
   }
 }
@@ -344,7 +356,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, const Quanti
       const bool mine = r >= before && r < (int64_t)incl;
       const unsigned who = __ballot_sync(0xffffffffu, mine);
       if (who == 0) {  // rank beyond the bucket (cannot happen for consistent histograms): last bin
-        if (lane == 31) { R.rank[warp] = 0; R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)((1u << w) - 1u); }
+        if (lane == 31) { R.rank[warp] = 0; R.bcount[warp] = 0; R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)((1u << w) - 1u); }
       } else if (lane == __ffs(who) - 1) {
         int64_t rr = r - before;
         int k = 0;
@@ -353,6 +365,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, const Quanti
           rr -= c[k];
         }
         R.rank[warp] = rr;
+        R.bcount[warp] = c[k];
         R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)(lane * 8 + k);
       }
     }
@@ -374,7 +387,10 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, const Quanti
       // groups of the next pass (targets are rank-sorted, so prefixes are sorted)
       int g = 0;
       for (int t = 0; t < nt; ++t) {
-        if (t == 0 || R.prefix[t] != R.uprefix[g - 1]) R.uprefix[g++] = R.prefix[t];
+        if (t == 0 || R.prefix[t] != R.uprefix[g - 1]) {
+          R.gbig[g] = R.bcount[t] > kBigBucket;
+          R.uprefix[g++] = R.prefix[t];
+        }
         R.group[t] = g - 1;
       }
       R.n_groups = g < 1 ? 1 : g;
@@ -424,49 +440,52 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(const double* __restr
   const int tid = threadIdx.x;
   const int nt = 2 * spec.n_q;
   const int rb = R.rb;
-  if (rb < 64 && R.n_valid > 0 && !R.overflow) {
-    const int nc = R.n_cand;
-    int m = 32;
-    while (m < nc) m <<= 1;
-    const double* __restrict__ c = cand + (size_t)blockIdx.x * kCandCap;
-    for (int i = tid; i < m; i += kTailThreads) s_keys[i] = i < nc ? key_of(c[i]) : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= m; k <<= 1) {          // bitonic sort, ascending
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < m; i += kTailThreads) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const uint64_t a = s_keys[i], b = s_keys[ixj];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    if (tid < nt) {
-      // candidates of this target = keys sharing its resolved prefix; they are contiguous in
-      // the sorted list and its residual rank counts from the first of them
-      const uint64_t lo_key = R.prefix[tid] << (64 - rb);
-      int lo = 0, hi = nc;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_keys[mid] < lo_key) lo = mid + 1; else hi = mid;
-      }
-      const int64_t at = lo + R.rank[tid];
-      R.prefix[tid] = s_keys[at < nc ? at : nc - 1];
-    }
-    __syncthreads();
-  } else if (rb < 64 && R.n_valid > 0) {
+  if (rb < 64 && R.n_valid > 0) {
+    // which targets can be read off the gathered list / off a one-value bucket, and is a scan needed?
     if (tid == 0) need_scan = 0;
     __syncthreads();
     if (tid < nt) {
       const int g = R.group[tid];
-      if (R.gmin[g] != R.gmax[g]) need_scan = 1;
+      if (R.gbig[g] ? (R.gmin[g] != R.gmax[g]) : (R.overflow != 0)) need_scan = 1;
     }
     __syncthreads();
     if (!need_scan) {
-      if (tid < nt) R.prefix[tid] = R.gmin[R.group[tid]];
+      const int nc = R.n_cand;
+      int m = 32;
+      while (m < nc) m <<= 1;
+      const double* __restrict__ c = cand + (size_t)blockIdx.x * kCandCap;
+      for (int i = tid; i < m; i += kTailThreads) s_keys[i] = i < nc ? key_of(c[i]) : ~0ull;
+      __syncthreads();
+      for (int k = 2; k <= m; k <<= 1) {          // bitonic sort, ascending
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < m; i += kTailThreads) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const uint64_t a = s_keys[i], b = s_keys[ixj];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (tid < nt) {
+        const int g = R.group[tid];
+        if (R.gbig[g]) {
+          R.prefix[tid] = R.gmin[g];            // a bucket of one repeated value
+        } else {
+          // candidates of this target = keys sharing its resolved prefix; they are contiguous
+          // in the sorted list and its residual rank counts from the first of them
+          const uint64_t lo_key = R.prefix[tid] << (64 - rb);
+          int lo = 0, hi = nc;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_keys[mid] < lo_key) lo = mid + 1; else hi = mid;
+          }
+          const int64_t at = lo + R.rank[tid];
+          R.prefix[tid] = s_keys[at < nc ? at : nc - 1];
+        }
+      }
       __syncthreads();
     } else {
       uint32_t* sh = (uint32_t*)s_keys;
