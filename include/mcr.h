@@ -234,27 +234,54 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
                   const uint8_t* mask_dev, const double* q_host, int32_t n_q, uint32_t sel_flags,
                   double* out_dev, int64_t* counts_dev, void* stream);
 
+#define MCR_MAX_QUANTILES 16
+
+/* One row of a multi-row select: n doubles at values_dev, optional cohort mask, n_q <= 16
+ * ascending fractions (ignored with MCR_SEL_MEDIAN). Rows of one call may differ in all of
+ * these, so a whole batch's aggregations (medians of summary columns over different cohorts,
+ * final-balance quantiles, nominal / real / withdrawal-rate bands) run as ONE launch sequence. */
+typedef struct mcr_select_row {
+  const double* values_dev;
+  const uint8_t* mask_dev;
+  int64_t n;
+  int32_t n_q;
+  uint32_t flags; /* MCR_SEL_MEDIAN */
+  double q[MCR_MAX_QUANTILES];
+} mcr_select_row;
+
+/* out_dev[r * 16 + k] = k-th quantile of row r; counts_dev[r] (may be NULL) = valid elements. */
+int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_rows,
+                       double* out_dev, int64_t* counts_dev, void* stream);
+
 /* The same select one step at a time, for path shards spread over several GPUs:
  *   BEGIN; for pass in 0..7 { if pass == mcr_select_full_passes(): COLLECT ;
  *   HIST (local shard) ; all-reduce(sum) hist_dev across ranks ; ADVANCE } ; FINISH.
- * (COLLECT gathers the local elements that share a resolved prefix into a short candidate list
- * so the remaining digits do not rescan the rows.)
  * After the all-reduce every rank holds the GLOBAL digit histogram, so all ranks walk to the
- * same exact global order statistics without moving any path data. state_dev / hist_dev are
- * caller-owned device buffers of mcr_select_state_bytes(rows) / mcr_select_hist_bytes(rows)
- * bytes; hist_dev is an array of uint32 counts (all-reduce it as int32). */
+ * same exact global order statistics without moving any path data (COLLECT gathers the local
+ * elements that share a resolved prefix into a short list so the remaining digits do not
+ * rescan the rows). rows_host describes this rank's shard of every row (same order, n_q and
+ * flags on all ranks) and must be passed to every step; state_dev / hist_dev are caller-owned
+ * device buffers of mcr_select_state_bytes(n_rows) / mcr_select_hist_bytes(n_rows) bytes;
+ * hist_dev is an array of uint32 counts (all-reduce it as int32). Output layout as
+ * mcr_quantiles_rows. */
 #define MCR_SELECT_BEGIN 0
 #define MCR_SELECT_HIST 1
 #define MCR_SELECT_ADVANCE 2
 #define MCR_SELECT_FINISH 3
 #define MCR_SELECT_COLLECT 4
+/* Optional (BEGIN with pass = 1): after HIST of pass 0, EXTREMES_GET writes every row's local
+ * (min, max) key into out_dev as int64[n_rows][2] in an encoding whose element-wise MIN over
+ * ranks is the global pair; all-reduce(MIN) it and hand it back with EXTREMES_SET before
+ * ADVANCE 0. The select then skips the key bits all elements share (constant rows finish at
+ * once, concentrated rows need no extra scans). */
+#define MCR_SELECT_EXTREMES_GET 5
+#define MCR_SELECT_EXTREMES_SET 6
 int32_t mcr_select_full_passes(void);
 int64_t mcr_select_state_bytes(int32_t rows);
 int64_t mcr_select_hist_bytes(int32_t rows);
-int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const double* values_dev, int64_t n,
-                    int64_t ld, int32_t rows, const uint8_t* mask_dev, const double* q_host,
-                    int32_t n_q, uint32_t sel_flags, void* state_dev, void* hist_dev,
-                    double* out_dev, int64_t* counts_dev, void* stream);
+int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_row* rows_host,
+                    int32_t n_rows, void* state_dev, void* hist_dev, double* out_dev,
+                    int64_t* counts_dev, void* stream);
 
 /* rates[i] = first_year_real[i] / start[i] * 100 where start[i] > 1e-6 else NaN
  * (median_first_year_withdrawal_rate, backend/simulation.py:78-96). */

@@ -480,22 +480,60 @@ static int make_spec(mcr_ctx* ctx, const double* q_host, int32_t n_q, uint32_t s
   return MCR_OK;
 }
 
+static int make_descs(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_rows, std::vector<RowDesc>& d) {
+  if (!rows_host || n_rows <= 0 || n_rows > 65535) return fail(ctx, MCR_EINVAL, "n_rows must be in [1, 65535]");
+  d.resize((size_t)n_rows);
+  for (int r = 0; r < n_rows; ++r) {
+    const mcr_select_row& in = rows_host[r];
+    if (in.n < 0 || (!in.values_dev && in.n > 0)) return fail(ctx, MCR_EINVAL, "bad select row");
+    d[r].x = in.values_dev;
+    d[r].mask = in.mask_dev;
+    d[r].n = in.n;
+    if (int rc = make_spec(ctx, in.q, in.n_q, in.flags, d[r].spec)) return rc;
+  }
+  return MCR_OK;
+}
+
+int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_rows, double* out_dev,
+                       int64_t* counts_dev, void* stream) {
+  if (!ctx || !out_dev) return fail(ctx, MCR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::vector<RowDesc> d;
+  if (int rc = make_descs(ctx, rows_host, n_rows, d)) return rc;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
+  const size_t hb = quantile_hist_bytes(n_rows);
+  if (int rc = ensure_scratch(ctx, hb + quantile_state_bytes(n_rows))) return rc;
+  int n_launches = 0;
+  MCR_CUDA(ctx, launch_quantiles_rows(n_rows, d.data(), out_dev, MCR_MAX_QUANTILES, counts_dev,
+                                      (char*)ctx->scratch + hb, ctx->scratch, (cudaStream_t)stream, &n_launches));
+  ctx->launches += n_launches;
+  return MCR_OK;
+}
+
 int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld, int32_t rows, const uint8_t* mask_dev,
                   const double* q_host, int32_t n_q, uint32_t sel_flags, double* out_dev, int64_t* counts_dev,
                   void* stream) {
   if (!ctx || (!values_dev && n > 0) || !out_dev) return fail(ctx, MCR_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (n < 0 || rows < 0 || (rows > 1 && ld < n)) return fail(ctx, MCR_EINVAL, "bad shape");
+  if (n < 0 || rows < 0 || rows > 65535 || (rows > 1 && ld < n)) return fail(ctx, MCR_EINVAL, "bad shape");
   QuantileSpec spec;
   if (int rc = make_spec(ctx, q_host, n_q, sel_flags, spec)) return rc;
   if (rows == 0) return MCR_OK;
+  std::vector<RowDesc> d((size_t)rows);
+  for (int r = 0; r < rows; ++r) {
+    d[r].x = values_dev + (int64_t)r * ld;
+    d[r].mask = mask_dev;
+    d[r].n = n;
+    d[r].spec = spec;
+  }
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
   const size_t hb = quantile_hist_bytes(rows);
   if (int rc = ensure_scratch(ctx, hb + quantile_state_bytes(rows))) return rc;
   int n_launches = 0;
-  MCR_CUDA(ctx, launch_quantiles(values_dev, n, ld, rows, mask_dev, spec, out_dev, counts_dev,
-                                 (char*)ctx->scratch + hb, ctx->scratch, (cudaStream_t)stream, &n_launches));
+  MCR_CUDA(ctx, launch_quantiles_rows(rows, d.data(), out_dev, n_q, counts_dev, (char*)ctx->scratch + hb, ctx->scratch,
+                                      (cudaStream_t)stream, &n_launches));
   ctx->launches += n_launches;
   return MCR_OK;
 }
@@ -504,36 +542,44 @@ int64_t mcr_select_state_bytes(int32_t rows) { return (int64_t)quantile_state_by
 int64_t mcr_select_hist_bytes(int32_t rows) { return (int64_t)quantile_hist_bytes(rows); }
 int32_t mcr_select_full_passes(void) { return select_full_passes(); }
 
-int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const double* values_dev, int64_t n, int64_t ld,
-                    int32_t rows, const uint8_t* mask_dev, const double* q_host, int32_t n_q, uint32_t sel_flags,
+int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_row* rows_host, int32_t n_rows,
                     void* state_dev, void* hist_dev, double* out_dev, int64_t* counts_dev, void* stream) {
   if (!ctx || !state_dev || !hist_dev) return fail(ctx, MCR_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (n < 0 || rows <= 0 || (rows > 1 && ld < n) || pass < 0 || pass > 7) return fail(ctx, MCR_EINVAL, "bad shape");
-  QuantileSpec spec;
-  if (int rc = make_spec(ctx, q_host, n_q, sel_flags, spec)) return rc;
+  if (pass < 0 || pass > 7) return fail(ctx, MCR_EINVAL, "bad pass");
+  std::vector<RowDesc> d;
+  if (int rc = make_descs(ctx, rows_host, n_rows, d)) return rc;
+  int64_t max_n = 0;
+  int max_nq = 1;
+  for (const RowDesc& r : d) {
+    max_n = r.n > max_n ? r.n : max_n;
+    max_nq = r.spec.n_q > max_nq ? r.spec.n_q : max_nq;
+  }
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   switch (step) {
-    case MCR_SELECT_BEGIN:
-      MCR_CUDA(ctx, launch_sel_begin(rows, state_dev, hist_dev, st));
+    case MCR_SELECT_BEGIN:  // pass != 0: the caller will exchange the row extremes after HIST 0
+      MCR_CUDA(ctx, launch_sel_begin(n_rows, d.data(), state_dev, hist_dev, st, /*adaptive=*/pass != 0));
+      break;
+    case MCR_SELECT_EXTREMES_GET:
+    case MCR_SELECT_EXTREMES_SET:
+      if (!out_dev) return fail(ctx, MCR_EINVAL, "null extremes buffer");
+      MCR_CUDA(ctx, launch_sel_extremes(n_rows, state_dev, (long long*)out_dev, step == MCR_SELECT_EXTREMES_SET, st));
       break;
     case MCR_SELECT_HIST:
-      if (!values_dev && n > 0) return fail(ctx, MCR_EINVAL, "null values");
-      MCR_CUDA(ctx, launch_sel_hist(values_dev, n, ld, rows, mask_dev, pass, state_dev, hist_dev, st));
+      MCR_CUDA(ctx, launch_sel_hist(n_rows, max_n, pass, state_dev, hist_dev, st));
       break;
     case MCR_SELECT_COLLECT:
-      if (!values_dev && n > 0) return fail(ctx, MCR_EINVAL, "null values");
-      MCR_CUDA(ctx, launch_sel_collect(values_dev, n, ld, rows, mask_dev, state_dev, st));
+      MCR_CUDA(ctx, launch_sel_collect(n_rows, max_n, state_dev, st));
       ctx->launches += 1;
       break;
     case MCR_SELECT_ADVANCE:
-      MCR_CUDA(ctx, launch_sel_advance(rows, spec, pass, state_dev, hist_dev, st));
+      MCR_CUDA(ctx, launch_sel_advance(n_rows, max_nq, pass, state_dev, hist_dev, st));
       break;
     case MCR_SELECT_FINISH:
       if (!out_dev) return fail(ctx, MCR_EINVAL, "null output");
-      MCR_CUDA(ctx, launch_sel_finish(rows, spec, state_dev, out_dev, counts_dev, st));
+      MCR_CUDA(ctx, launch_sel_finish(n_rows, state_dev, out_dev, MCR_MAX_QUANTILES, counts_dev, st));
       break;
     default:
       return fail(ctx, MCR_EINVAL, "bad select step");

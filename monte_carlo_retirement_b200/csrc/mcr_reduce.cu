@@ -58,6 +58,7 @@ __device__ __forceinline__ double value_of(uint64_t k) {
 // Layout: hist[rows][kMaxTargets][256] u32 is its own contiguous array (the all-reduced
 // buffer); the rest of the state is SelRow[rows] followed by the candidate lists.
 struct SelRow {
+  RowDesc d;                        // what this row selects from / for (copied in by BEGIN)
   uint64_t prefix[kMaxTargets];     // per target (rank-sorted): the `rb` key bits resolved so far
   int64_t rank[kMaxTargets];        // per target: rank inside the current prefix bucket
   uint64_t uprefix[kMaxTargets];    // sorted unique prefixes (groups) of the current pass
@@ -74,7 +75,9 @@ struct SelRow {
   int32_t n_cand;                   // elements in this row's candidate list
   int32_t overflow;                 // candidate list overflowed
   int32_t collected;                // candidate list is valid
-  int32_t adaptive;
+  int32_t adaptive;                 // row extremes are available after pass 0
+  int32_t fused;                    // single-GPU call: k_sel_tail finishes the row (ungathered buckets allowed)
+  int32_t pad_;
 };
 
 constexpr int kHistThreads = 256;
@@ -84,13 +87,15 @@ constexpr int kBigBucket = 2048;    // buckets above this are not gathered (reso
 constexpr int kFullPasses = 3;      // passes that scan the rows before the collect
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 
-__global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, int adaptive) {
+__global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, const RowDesc* __restrict__ desc,
+                           int adaptive, int fused) {
   SelRow& R = rows[blockIdx.x];
+  if (threadIdx.x == 0) R.d = desc[blockIdx.x];
   uint32_t* H = hist + (size_t)blockIdx.x * kHistWords;
   for (int k = threadIdx.x; k < kHistWords; k += blockDim.x) H[k] = 0;
   if (threadIdx.x == 0) {
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
-    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive;
+    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
@@ -183,9 +188,7 @@ __device__ __forceinline__ void hist_scan(const double* __restrict__ x, const ui
 
 // One pass, first half: histogram of the next digit inside every live prefix bucket. Rows that
 // are finished skip; rows with a valid candidate list scan that list (one CTA).
-__global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restrict__ values, int64_t n, int64_t ld,
-                                                           const uint8_t* __restrict__ mask, SelRow* __restrict__ rows,
-                                                           uint32_t* __restrict__ hist,
+__global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
                                                            const double* __restrict__ cand, int pass) {
   extern __shared__ uint32_t sh[];  // [n_groups][256]
   __shared__ PrefixTable T;
@@ -194,12 +197,14 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restr
   if (rb >= 64) return;
   const bool from_cand = R.collected && !R.overflow;
   if (from_cand && blockIdx.x > 0) return;
+  const int64_t n = R.d.n;
+  if (!from_cand && (int64_t)blockIdx.x * kChunk >= n) return;
   const int ng = R.n_groups;
   uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
   for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
   if (rb > 0) build_table(T, R, ng); else __syncthreads();
-  const double* __restrict__ x = from_cand ? cand + (size_t)blockIdx.y * kCandCap : values + (int64_t)blockIdx.y * ld;
-  const uint8_t* __restrict__ m = from_cand ? nullptr : mask;
+  const double* __restrict__ x = from_cand ? cand + (size_t)blockIdx.y * kCandCap : R.d.x;
+  const uint8_t* __restrict__ m = from_cand ? nullptr : R.d.mask;
   const int w = 64 - rb < 8 ? 64 - rb : 8;
   const int64_t begin = from_cand ? 0 : (int64_t)blockIdx.x * kChunk;
   const int64_t stop = from_cand ? (int64_t)R.n_cand : (begin + kChunk < n ? begin + kChunk : n);
@@ -211,9 +216,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(const double* __restr
 }
 
 // After kFullPasses passes: gather the elements that share a live prefix into the row's list.
-__global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __restrict__ values, int64_t n, int64_t ld,
-                                                              const uint8_t* __restrict__ mask,
-                                                              SelRow* __restrict__ rows, double* __restrict__ cand) {
+__global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand) {
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
   __shared__ int s_full;
@@ -221,6 +224,9 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __re
   SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
   if (rb >= 64 || R.collected) return;
+  const int64_t n = R.d.n;
+  if ((int64_t)blockIdx.x * kChunk >= n) return;
+  const uint8_t* __restrict__ mask = R.d.mask;
   const int ng = R.n_groups;
   if (threadIdx.x < kMaxTargets) {
     s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __re
   }
   if (threadIdx.x == 0) s_full = 0;
   build_table(T, R, ng);
-  const double* __restrict__ x = values + (int64_t)blockIdx.y * ld;
+  const double* __restrict__ x = R.d.x;
   double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
   const int64_t begin = (int64_t)blockIdx.x * kChunk;
   const int64_t stop = begin + kChunk < n ? begin + kChunk : n;
@@ -267,13 +273,30 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(const double* __re
   if (threadIdx.x == 0 && s_full) R.overflow = 1;
 }
 
+// Row extremes <-> a caller buffer ext[rows][2] of int64 in an order-preserving signed encoding
+// chosen so that ONE all-reduce(MIN) across ranks yields the global min and max:
+//   ext[r][0] = kmin ^ 2^63,  ext[r][1] = ~kmax ^ 2^63   (min over ranks of ~kmax == ~max kmax)
+__global__ void k_sel_extremes(SelRow* __restrict__ rows, long long* __restrict__ ext, int n_rows, int store) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  SelRow& R = rows[r];
+  const unsigned long long top = 0x8000000000000000ull;
+  if (!store) {
+    ext[2 * r] = (long long)(R.kmin ^ top);
+    ext[2 * r + 1] = (long long)((~R.kmax) ^ top);
+  } else {
+    R.kmin = (unsigned long long)ext[2 * r] ^ top;
+    R.kmax = ~((unsigned long long)ext[2 * r + 1] ^ top);
+  }
+}
+
 __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   SelRow& R = rows[blockIdx.x];
   if (threadIdx.x == 0 && R.rb < 64 && !R.collected) {
     if (R.n_cand > kCandCap) { R.n_cand = kCandCap; R.overflow = 1; }
     // stepwise (multi-GPU) protocol: later passes histogram the list, so a row with a bucket
     // that was not gathered keeps scanning the full row instead
-    if (!R.adaptive)
+    if (!R.fused)
       for (int g = 0; g < R.n_groups; ++g)
         if (R.gbig[g]) R.overflow = 1;
     R.collected = 1;
@@ -282,7 +305,8 @@ __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
 
 // One pass, second half (one warp per target + housekeeping): consume the merged histogram H
 // of row R. Needs >= 32 * (2 * n_q) threads; ends with H cleared and the next pass's groups set.
-__device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, const QuantileSpec& spec, int pass) {
+__device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
+  const QuantileSpec& spec = R.d.spec;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int nq = spec.n_q, nt = 2 * nq;
@@ -401,12 +425,13 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, const Quanti
 }
 
 __global__ void __launch_bounds__(1024) k_sel_advance(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
-                                                      QuantileSpec spec, int pass) {
-  advance_row(rows[blockIdx.x], hist + (size_t)blockIdx.x * kHistWords, spec, pass);
+                                                      int pass) {
+  advance_row(rows[blockIdx.x], hist + (size_t)blockIdx.x * kHistWords, pass);
 }
 
 // numpy 'linear' interpolation / np.median rule for quantile `k` of a finished row
-__device__ __forceinline__ double finish_value(const SelRow& R, const QuantileSpec& spec, int k) {
+__device__ __forceinline__ double finish_value(const SelRow& R, int k) {
+  const QuantileSpec& spec = R.d.spec;
   const int64_t nv = R.n_valid;
   if (nv <= 0) return CUDART_NAN;
   const double a = value_of(R.prefix[R.slot[2 * k]]);
@@ -429,14 +454,16 @@ __device__ __forceinline__ double finish_value(const SelRow& R, const QuantileSp
 // off the sorted list; an overflowed bucket of one repeated value is resolved by its extremes;
 // an overflowed bucket of distinct values scans the full row here (slow, rare).
 constexpr int kTailThreads = 1024;
-__global__ void __launch_bounds__(kTailThreads) k_sel_tail(const double* __restrict__ values, int64_t n, int64_t ld,
-                                                           const uint8_t* __restrict__ mask, SelRow* __restrict__ rows,
-                                                           const double* __restrict__ cand, QuantileSpec spec,
-                                                           double* __restrict__ out, int64_t* __restrict__ counts) {
+__global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ rows, const double* __restrict__ cand,
+                                                           double* __restrict__ out, int out_stride,
+                                                           int64_t* __restrict__ counts) {
   extern __shared__ uint64_t s_keys[];  // kCandCap keys (64 KB), reused as the histogram on the slow path
   __shared__ PrefixTable T;
   __shared__ int need_scan;
   SelRow& R = rows[blockIdx.x];
+  const QuantileSpec& spec = R.d.spec;
+  const int64_t n = R.d.n;
+  const uint8_t* __restrict__ mask = R.d.mask;
   const int tid = threadIdx.x;
   const int nt = 2 * spec.n_q;
   const int rb = R.rb;
@@ -489,7 +516,7 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(const double* __restr
       __syncthreads();
     } else {
       uint32_t* sh = (uint32_t*)s_keys;
-      const double* __restrict__ x = values + (int64_t)blockIdx.x * ld;
+      const double* __restrict__ x = R.d.x;
       for (int pass = kFullPasses; R.rb < 64; ++pass) {
         const int cur = R.rb;
         const int w = 64 - cur < 8 ? 64 - cur : 8;
@@ -497,18 +524,18 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(const double* __restr
         build_table(T, R, R.n_groups);
         hist_scan(x, mask, 0, n, kTailThreads, cur, w, T, sh, nullptr, nullptr);
         __syncthreads();
-        advance_row(R, sh, spec, pass);
+        advance_row(R, sh, pass);
       }
     }
   }
-  if (tid < spec.n_q) out[(int64_t)blockIdx.x * spec.n_q + tid] = finish_value(R, spec, tid);
+  if (tid < spec.n_q) out[(int64_t)blockIdx.x * out_stride + tid] = finish_value(R, tid);
   if (tid == 0 && counts) counts[blockIdx.x] = R.n_valid;
 }
 
-__global__ void k_sel_finish(const SelRow* __restrict__ rows, QuantileSpec spec, double* __restrict__ out,
+__global__ void k_sel_finish(const SelRow* __restrict__ rows, double* __restrict__ out, int out_stride,
                              int64_t* __restrict__ counts) {
   const SelRow& R = rows[blockIdx.x];
-  if (threadIdx.x < spec.n_q) out[(int64_t)blockIdx.x * spec.n_q + threadIdx.x] = finish_value(R, spec, threadIdx.x);
+  if (threadIdx.x < R.d.spec.n_q) out[(int64_t)blockIdx.x * out_stride + threadIdx.x] = finish_value(R, threadIdx.x);
   if (threadIdx.x == 0 && counts) counts[blockIdx.x] = R.n_valid;
 }
 
@@ -648,69 +675,83 @@ cudaError_t launch_fp64_peak(int sm_count, int iters, double* sink, cudaStream_t
 
 size_t quantile_state_bytes(int rows) {
   const size_t r = (size_t)(rows > 0 ? rows : 1);
-  return sizeof(SelRow) * r + sizeof(double) * kCandCap * r;  // state + candidate lists
+  return sizeof(SelRow) * r + sizeof(double) * kCandCap * r + sizeof(RowDesc) * r;  // state, candidate lists, descriptors
 }
 size_t quantile_hist_bytes(int rows) { return sizeof(uint32_t) * kHistWords * (size_t)(rows > 0 ? rows : 1); }
 static double* cand_of(void* state, int rows) { return (double*)((char*)state + sizeof(SelRow) * (size_t)rows); }
+static RowDesc* desc_of(void* state, int rows) {
+  return (RowDesc*)((char*)state + (sizeof(SelRow) + sizeof(double) * kCandCap) * (size_t)rows);
+}
 
-cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive) {
-  if (rows > 0) k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist, adaptive);
+cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, void* hist, cudaStream_t st, int adaptive,
+                             int fused) {
+  if (rows <= 0) return cudaSuccess;
+  // pageable source: staged before the call returns
+  cudaError_t e = cudaMemcpyAsync(desc_of(state, rows), desc_host, sizeof(RowDesc) * (size_t)rows,
+                                  cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist, desc_of(state, rows), adaptive, fused);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sel_hist(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, int pass,
-                            void* state, void* hist, cudaStream_t st) {
-  const unsigned chunks = (unsigned)((n + kChunk - 1) / kChunk);
+cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st) {
+  const unsigned chunks = (unsigned)((max_n + kChunk - 1) / kChunk);
   if (rows <= 0 || chunks == 0) return cudaSuccess;
   const size_t smem = (size_t)kHistWords * sizeof(uint32_t);
-  k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>(values, n, ld, mask, (SelRow*)state,
-                                                                       (uint32_t*)hist, cand_of(state, rows), pass);
+  k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>((SelRow*)state, (uint32_t*)hist,
+                                                                       cand_of(state, rows), pass);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sel_collect(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, void* state,
-                               cudaStream_t st) {
-  const unsigned chunks = (unsigned)((n + kChunk - 1) / kChunk);
+cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st) {
+  const unsigned chunks = (unsigned)((max_n + kChunk - 1) / kChunk);
   if (rows <= 0) return cudaSuccess;
-  if (chunks > 0)
-    k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>(values, n, ld, mask, (SelRow*)state,
-                                                                         cand_of(state, rows));
+  if (chunks > 0) k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>((SelRow*)state, cand_of(state, rows));
   k_sel_collect_finish<<<rows, 32, 0, st>>>((SelRow*)state);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sel_advance(int rows, const QuantileSpec& spec, int pass, void* state, void* hist, cudaStream_t st) {
-  if (rows > 0) k_sel_advance<<<rows, 32 * 2 * spec.n_q, 0, st>>>((SelRow*)state, (uint32_t*)hist, spec, pass);
+cudaError_t launch_sel_advance(int rows, int max_nq, int pass, void* state, void* hist, cudaStream_t st) {
+  if (rows > 0) k_sel_advance<<<rows, 32 * 2 * max_nq, 0, st>>>((SelRow*)state, (uint32_t*)hist, pass);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sel_finish(int rows, const QuantileSpec& spec, const void* state, double* out, int64_t* counts,
-                              cudaStream_t st) {
-  if (rows > 0) k_sel_finish<<<rows, 32, 0, st>>>((const SelRow*)state, spec, out, counts);
+cudaError_t launch_sel_extremes(int rows, void* state, long long* ext, int store, cudaStream_t st) {
+  if (rows > 0) k_sel_extremes<<<(rows + 127) / 128, 128, 0, st>>>((SelRow*)state, ext, rows, store);
   return cudaGetLastError();
 }
 
-cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask,
-                             const QuantileSpec& spec, double* out, int64_t* counts, void* state, void* hist,
-                             cudaStream_t st, int* n_launches) {
+cudaError_t launch_sel_finish(int rows, const void* state, double* out, int out_stride, int64_t* counts, cudaStream_t st) {
+  if (rows > 0) k_sel_finish<<<rows, 32, 0, st>>>((const SelRow*)state, out, out_stride, counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* out, int out_stride, int64_t* counts,
+                                  void* state, void* hist, cudaStream_t st, int* n_launches) {
   *n_launches = 0;
   if (rows <= 0) return cudaSuccess;
-  cudaError_t e = launch_sel_begin(rows, state, hist, st, /*adaptive=*/1);
+  int64_t max_n = 0;
+  int max_nq = 1;
+  for (int r = 0; r < rows; ++r) {
+    max_n = desc_host[r].n > max_n ? desc_host[r].n : max_n;
+    max_nq = desc_host[r].spec.n_q > max_nq ? desc_host[r].spec.n_q : max_nq;
+  }
+  cudaError_t e = launch_sel_begin(rows, desc_host, state, hist, st, /*adaptive=*/1, /*fused=*/1);
   ++*n_launches;
   for (int pass = 0; pass < kFullPasses && e == cudaSuccess; ++pass) {
-    e = launch_sel_hist(values, n, ld, rows, mask, pass, state, hist, st);
-    *n_launches += n > 0;
-    if (e == cudaSuccess) e = launch_sel_advance(rows, spec, pass, state, hist, st);
+    e = launch_sel_hist(rows, max_n, pass, state, hist, st);
+    *n_launches += max_n > 0;
+    if (e == cudaSuccess) e = launch_sel_advance(rows, max_nq, pass, state, hist, st);
     ++*n_launches;
   }
-  if (e == cudaSuccess) e = launch_sel_collect(values, n, ld, rows, mask, state, st);
-  *n_launches += 1 + (n > 0);
+  if (e == cudaSuccess) e = launch_sel_collect(rows, max_n, state, st);
+  *n_launches += 1 + (max_n > 0);
   if (e != cudaSuccess) return e;
   // one launch for the remaining digits + interpolation (see k_sel_tail)
   e = cudaFuncSetAttribute(k_sel_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * kCandCap));
   if (e != cudaSuccess) return e;
-  k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>(values, n, ld, mask, (SelRow*)state,
-                                                                      cand_of(state, rows), spec, out, counts);
+  k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>((SelRow*)state, cand_of(state, rows), out,
+                                                                      out_stride, counts);
   ++*n_launches;
   return cudaGetLastError();
 }

@@ -15,21 +15,29 @@ struct QuantileSpec {
   double q[kMaxQuantiles];
 };
 
+// one row of a select call: where the values are, the cohort mask, what is asked
+struct RowDesc {
+  const double* x;
+  const uint8_t* mask;
+  int64_t n;
+  QuantileSpec spec;
+};
+
+// all rows in ONE launch sequence (rows may differ in source, length, mask and quantiles)
+cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* out, int out_stride, int64_t* counts,
+                                  void* state, void* hist, cudaStream_t st, int* n_launches);
+// the same select, one pass at a time (a multi-GPU caller all-reduces `hist` between hist and advance)
+cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, void* hist, cudaStream_t st,
+                             int adaptive = 0, int fused = 0);
+cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st);
+cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st);
+int select_full_passes();
+cudaError_t launch_sel_extremes(int rows, void* state, long long* ext, int store, cudaStream_t st);
+cudaError_t launch_sel_advance(int rows, int max_nq, int pass, void* state, void* hist, cudaStream_t st);
+cudaError_t launch_sel_finish(int rows, const void* state, double* out, int out_stride, int64_t* counts,
+                              cudaStream_t st);
 size_t quantile_state_bytes(int rows);
 size_t quantile_hist_bytes(int rows);
-cudaError_t launch_quantiles(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask,
-                             const QuantileSpec& spec, double* out, int64_t* counts, void* state, void* hist,
-                             cudaStream_t st, int* n_launches);
-// the same select, one pass at a time (a multi-GPU caller all-reduces `hist` between hist and advance)
-cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive = 0);
-cudaError_t launch_sel_hist(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, int pass,
-                            void* state, void* hist, cudaStream_t st);
-cudaError_t launch_sel_collect(const double* values, int64_t n, int64_t ld, int rows, const uint8_t* mask, void* state,
-                               cudaStream_t st);
-int select_full_passes();
-cudaError_t launch_sel_advance(int rows, const QuantileSpec& spec, int pass, void* state, void* hist, cudaStream_t st);
-cudaError_t launch_sel_finish(int rows, const QuantileSpec& spec, const void* state, double* out, int64_t* counts,
-                              cudaStream_t st);
 cudaError_t launch_rates(const double* start, const double* fy_real, int64_t n, double* rates, cudaStream_t st);
 cudaError_t launch_minmax(const double* x, const uint8_t* mask, int64_t n, double divisor, unsigned long long* keys2,
                           double* minmax, cudaStream_t st);

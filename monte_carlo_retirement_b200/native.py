@@ -82,6 +82,28 @@ class Outputs(C.Structure):
     ]
 
 
+class SelectRow(C.Structure):
+    _fields_ = [
+        ("values_dev", C.c_void_p),
+        ("mask_dev", C.c_void_p),
+        ("n", C.c_int64),
+        ("n_q", C.c_int32),
+        ("flags", C.c_uint32),
+        ("q", C.c_double * 16),
+    ]
+
+
+def _select_row_dtype():
+    import numpy as np
+
+    return np.dtype([("values_dev", "<u8"), ("mask_dev", "<u8"), ("n", "<i8"), ("n_q", "<i4"), ("flags", "<u4"),
+                     ("q", "<f8", (16,))])
+
+
+SELECT_ROW_DTYPE = _select_row_dtype()
+assert SELECT_ROW_DTYPE.itemsize == C.sizeof(SelectRow)
+
+
 class PathRecord(C.Structure):
     _fields_ = [
         ("start_balance", C.c_double),
@@ -118,8 +140,8 @@ SIGNATURES = {
     "mcr_select_state_bytes": (_I64, [_I32]),
     "mcr_select_hist_bytes": (_I64, [_I32]),
     "mcr_select_full_passes": (_I32, []),
-    "mcr_select_step": (C.c_int, [_VP, _I32, _I32, _VP, _I64, _I64, _I32, _VP, C.POINTER(_D), _I32, _U32, _VP, _VP,
-                                  _VP, _VP, _VP]),
+    "mcr_quantiles_rows": (C.c_int, [_VP, C.POINTER(SelectRow), _I32, _VP, _VP, _VP]),
+    "mcr_select_step": (C.c_int, [_VP, _I32, _I32, C.POINTER(SelectRow), _I32, _VP, _VP, _VP, _VP, _VP]),
     "mcr_first_year_rates": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP]),
     "mcr_minmax": (C.c_int, [_VP, _VP, _VP, _I64, _D, _VP, _VP]),
     "mcr_histogram": (C.c_int, [_VP, _VP, _VP, _I64, _D, _I32, _I32, _VP, _VP, _VP]),
@@ -267,32 +289,86 @@ class Context:
         self._check(self.lib.mcr_quantiles(self.handle, _ptr(values), n, ld, rows, _ptr(mask), qs, len(q),
                                            SEL_MEDIAN if median else 0, _ptr(out), _ptr(counts), _stream_handle()))
 
-    def quantiles_distributed(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, all_reduce,
-                              counts=None, mask=None, median: bool = False) -> None:
-        """Exact GLOBAL quantiles over path shards held by several ranks: `all_reduce(tensor)`
-        must sum an int32 device tensor in place across ranks (torch.distributed.all_reduce)."""
+    @staticmethod
+    def select_rows(specs):
+        """Row descriptors (mcr_select_row[]) as one numpy structured array, filled group-wise.
+        A spec is (tensor, n, mask_or_None, quantiles, median): a 1-D tensor is one row, a 2-D
+        time-major [rows, ld] tensor contributes one row per tensor row."""
+        import numpy as np
+
+        groups = []
+        total = 0
+        for x, n, mask, q, median in specs:
+            rows = int(x.shape[0]) if (x is not None and x.dim() == 2) else 1
+            groups.append((x, int(n), mask, q, median, rows))
+            total += rows
+        arr = np.zeros(total, dtype=SELECT_ROW_DTYPE)
+        at = 0
+        for x, n, mask, q, median, rows in groups:
+            sl = arr[at:at + rows]
+            if n > 0:
+                base = int(x.data_ptr())
+                stride = int(x.stride(0)) * 8 if x.dim() == 2 else 0
+                sl["values_dev"] = base + stride * np.arange(rows, dtype=np.uint64)
+            sl["mask_dev"] = 0 if mask is None else int(mask.data_ptr())
+            sl["n"] = n
+            sl["n_q"] = len(q)
+            sl["flags"] = SEL_MEDIAN if median else 0
+            sl["q"][:, :len(q)] = np.asarray(q, dtype=np.float64)
+            at += rows
+        return arr
+
+    @staticmethod
+    def series_rows(series, n: int, rows: int, q, mask=None, median: bool = False):
+        """Select spec for the rows of a time-major [rows, ld] series tensor."""
+        return [(series[:rows], n, mask, q, median)]
+
+    def quantiles_rows(self, specs, out, counts=None, all_reduce=None, all_reduce_min=None) -> None:
+        """All rows of `specs` in one launch sequence; out is a [n_rows, 16] f64 device tensor.
+        With `all_reduce` (sums an int32 device tensor in place across ranks) the rows are this
+        rank's shards and every rank obtains the exact GLOBAL quantiles; `all_reduce_min`
+        (element-wise MIN of an int64 device tensor) additionally enables the adaptive start."""
         import torch
 
-        dev = values.device
-        state = torch.empty(int(self.lib.mcr_select_state_bytes(rows)), dtype=torch.uint8, device=dev)
-        hist = torch.empty(int(self.lib.mcr_select_hist_bytes(rows)) // 4, dtype=torch.int32, device=dev)
-        qs = (_D * len(q))(*[float(v) for v in q])
-        flags = SEL_MEDIAN if median else 0
+        arr_np = specs if hasattr(specs, "dtype") else self.select_rows(specs)
+        n_rows = len(arr_np)
+        arr = C.cast(arr_np.ctypes.data, C.POINTER(SelectRow))
+        if all_reduce is None:
+            self._check(self.lib.mcr_quantiles_rows(self.handle, arr, n_rows, _ptr(out), _ptr(counts), _stream_handle()))
+            return
+        dev = out.device
+        state = torch.empty(int(self.lib.mcr_select_state_bytes(n_rows)), dtype=torch.uint8, device=dev)
+        hist = torch.empty(int(self.lib.mcr_select_hist_bytes(n_rows)) // 4, dtype=torch.int32, device=dev)
 
-        def step(kind, p=0):
-            self._check(self.lib.mcr_select_step(self.handle, kind, p, _ptr(values), n, ld, rows, _ptr(mask), qs,
-                                                 len(q), flags, _ptr(state), _ptr(hist), _ptr(out), _ptr(counts),
-                                                 _stream_handle()))
+        def step(kind, p=0, buf=None):
+            self._check(self.lib.mcr_select_step(self.handle, kind, p, arr, n_rows, _ptr(state), _ptr(hist),
+                                                 _ptr(out if buf is None else buf), _ptr(counts), _stream_handle()))
 
         full = int(self.lib.mcr_select_full_passes())
-        step(0)
+        adaptive = all_reduce_min is not None
+        step(0, 1 if adaptive else 0)
         for p in range(8):
             if p == full:
                 step(4)  # COLLECT: candidates of the resolved prefixes (local shard)
             step(1, p)
+            if p == 0 and adaptive:  # global row extremes -> skip the key bits every element shares
+                ext = torch.empty((n_rows, 2), dtype=torch.int64, device=dev)
+                step(5, 0, ext)
+                all_reduce_min(ext)
+                step(6, 0, ext)
             all_reduce(hist)
             step(2, p)
         step(3)
+
+    def quantiles_distributed(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, all_reduce,
+                              counts=None, mask=None, median: bool = False) -> None:
+        """Uniform-rows convenience over quantiles_rows(all_reduce=...): out is [rows, len(q)]."""
+        import torch
+
+        specs = [(values[:rows] if values.dim() == 2 else values, n, mask, q, median)]
+        tmp = torch.empty((rows, 16), dtype=torch.float64, device=out.device)
+        self.quantiles_rows(specs, tmp, counts=counts, all_reduce=all_reduce)
+        out.view(-1)[: rows * len(q)].view(rows, len(q)).copy_(tmp[:, : len(q)])
 
     def first_year_rates(self, start, fy_real, n: int, rates) -> None:
         self._check(self.lib.mcr_first_year_rates(self.handle, _ptr(start), _ptr(fy_real), n, _ptr(rates),

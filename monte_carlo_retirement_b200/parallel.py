@@ -110,45 +110,26 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def _reduce_counts(self, counts):
         return self.coll.sum_(counts)
 
-    # ---- aggregate-only mode over the global path set ------------------------------------------
-    def aggregates_device(self, working_months: int, num_simulations: int, *, bands: bool = True,
-                          first_path: int = 0, timeline_events=None):
+    # ---- hooks: the base class's aggregate-only path runs unchanged on the local shard, with the
+    # ---- few collectives injected here ------------------------------------------------------------
+    def _shard(self, n_global: int) -> Tuple[int, int]:
+        return shard_range(int(n_global), self.coll.rank, self.coll.world)
+
+    def _agree(self, flag: bool) -> bool:
         import torch
 
-        ctx = self.native_context
-        coll = self.coll
-        import os
+        t = torch.tensor([int(bool(flag))], dtype=torch.int32, device=self._torch_device())
+        return bool(self.coll.max_(t).item())
 
-        n_global = int(num_simulations)
-        lo, n = shard_range(n_global, coll.rank, coll.world)
-        series_bytes = 8 * n * (2 * self._trajectory_len(int(working_months)) + self.params_model.retirement_years)
-        free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
-        sweep_t = torch.tensor([int(bool(bands) and (series_bytes > 0.6 * free_bytes
-                                                       or os.environ.get("MCR_SERIES_SWEEP") == "1"))],
-                               dtype=torch.int32, device=self._torch_device())
-        sweep = bool(coll.max_(sweep_t).item())  # every rank takes the same route
-        if timeline_events is not None:
-            timeline_events[0].record()
-        b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=first_path + lo)
-        if timeline_events is not None:
-            timeline_events[1].record()
-        dev = b.cols.device
-        T, R = b.T, b.R
-        f64 = dict(dtype=torch.float64, device=dev)
-        nq, nw, nf = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES), len(FINAL_BALANCE_QUANTILES)
-        coll.sum_(b.counters)
-        rates = torch.empty(n, **f64)
-        ctx.first_year_rates(b.cols[0], b.cols[3], n, rates)
-        small = torch.empty(3 + nf + 4, **f64)
-        cnt = torch.empty(3, dtype=torch.int64, device=dev)
-        ar = coll.sum_
-        ctx.quantiles_distributed(rates, n, n, 1, [0.5], small[0:], ar, counts=cnt[0:], median=True)
-        ctx.quantiles_distributed(b.cols[0], n, n, 1, [0.5], small[1:], ar, counts=cnt[1:], median=True)
-        ctx.quantiles_distributed(b.cols[1], n, n, 1, [0.5], small[2:], ar, counts=cnt[2:], mask=b.success, median=True)
-        ctx.quantiles_distributed(b.cols[1], n, n, 1, FINAL_BALANCE_QUANTILES, small[3:], ar)
-        rng_m = small[3 + nf:3 + nf + 2]
-        rng_1 = small[3 + nf + 2:3 + nf + 4]
-        hists = torch.zeros(160, dtype=torch.int64, device=dev)
+    def _select(self, specs, out16, counts=None) -> None:
+        # exact GLOBAL order statistics: local digit histograms, all-reduced per pass
+        self.native_context.quantiles_rows(specs, out16, counts=counts, all_reduce=self.coll.sum_,
+                                           all_reduce_min=self.coll.min_)
+
+    def _final_balance_histograms(self, b, rng_m, rng_1, hists) -> None:
+        import torch
+
+        ctx, coll, n = self.native_context, self.coll, b.n
         for rng, divisor in ((rng_m, 1e6), (rng_1, 1.0)):
             ctx.minmax(b.cols[1], n, rng, mask=b.success, divisor=divisor)
             # global range: NaN (empty local cohort) must not poison min/max
@@ -162,41 +143,6 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
         ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
         coll.sum_(hists)
-        band_block = wr_counts = None
-        if bands:
-            band_block = torch.empty(2 * T * nq + R * nw, **f64)
-            wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-            if not sweep:
-                ctx.quantiles_distributed(b.traj, n, n, T, TRAJECTORY_QUANTILES, band_block[0:], ar)
-                ctx.quantiles_distributed(b.real, n, n, T, TRAJECTORY_QUANTILES, band_block[T * nq:], ar)
-                ctx.quantiles_distributed(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, band_block[2 * T * nq:], ar,
-                                          counts=wr_counts)
-            else:  # one series at a time (recompute): 1e9-path jobs, see simulation.aggregates_device
-                for which, rows, qs, off in (("traj", T, TRAJECTORY_QUANTILES, 0),
-                                             ("real", T, TRAJECTORY_QUANTILES, T * nq),
-                                             ("wr", R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)):
-                    part = self.run_batch_device(working_months, n, series=which, first_path=first_path + lo)
-                    ctx.quantiles_distributed(getattr(part, which), n, n, rows, qs, band_block[off:], ar,
-                                              counts=wr_counts if which == "wr" else None)
-                    torch.cuda.current_stream().synchronize()
-                    del part
-        self._last_batch = b
-        from .simulation import DeviceAggregates
-
-        b.n_global = n_global
-        agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
-                               wr_counts=wr_counts, rates=rates)
-        agg.n_override = n_global
-        return agg
-
-    def run_aggregates(self, working_months: int, num_simulations: int, *, bands: bool = True,
-                       first_path: int = 0) -> Dict[str, Any]:
-        agg = self.aggregates_device(working_months, num_simulations, bands=bands, first_path=first_path)
-        out = agg.to_host()
-        n = int(num_simulations)
-        out["num_simulations"] = n
-        out["success_probability"] = float(out["success_count"] / n * 100.0)
-        return out
 
     # ---- the reference's 7-tuple, global, on every rank ------------------------------------------
     def run_monte_carlo_simulations(self, working_months: int, num_simulations: int):
@@ -215,10 +161,7 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         real_bands = torch.empty((T, nq), **f64)
         wr_bands = torch.empty((R, nw), **f64)
         wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-        ar = coll.sum_
-        ctx.quantiles_distributed(b.traj, n, n, T, TRAJECTORY_QUANTILES, bands, ar)
-        ctx.quantiles_distributed(b.real, n, n, T, TRAJECTORY_QUANTILES, real_bands, ar)
-        ctx.quantiles_distributed(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, wr_bands, ar, counts=wr_counts)
+        self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)  # one distributed multi-row select
         # sample paths: each rank contributes the columns it owns, summed into a zero block
         cols = self._sample_columns(n_global)
         k = len(cols)
@@ -231,21 +174,36 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
             ctx.gather_columns(b.real, n, T, [c for _, c in mine], tmp)
             samples[1, [j for j, _ in mine]] = tmp
         coll.sum_(samples)
-        # summary columns of all shards, in global path order
+        # summary columns of all shards, in global path order: ONE all-gather of a packed
+        # [5 f64 | success | ruin] block per rank over NVLink, one pinned D2H, zero-copy DataFrame
         sizes = [shard_range(n_global, r, coll.world)[1] for r in range(coll.world)]
-        all_cols = coll.gather_cat(b.cols, dim=1, sizes=sizes).cpu().numpy()
-        all_succ = coll.gather_cat(b.success, dim=0, sizes=sizes).cpu().numpy().astype(bool)
-        all_ruin = coll.gather_cat(b.ruin, dim=0, sizes=sizes).cpu().numpy()
-        self.last_d2h_bytes = n_global * (5 * 8 + 1 + 4) + (2 * T * nq + R * nw + 2 * k * T + R) * 8
+        m = max(sizes)
+        packed = torch.zeros((7, m), **f64)
+        packed[0:5, :n] = b.cols
+        packed[5, :n] = b.success.to(torch.float64)
+        packed[6, :n] = b.ruin.to(torch.float64)
+        gathered = torch.empty((coll.world, 7, m), **f64)
+        coll.dist.all_gather_into_tensor(gathered, packed, group=coll.group)
+        host = torch.empty((7, n_global), dtype=torch.float64, pin_memory=True)
+        if all(sz == m for sz in sizes):
+            host.copy_(gathered.permute(1, 0, 2).reshape(7, -1), non_blocking=True)
+        else:
+            host.copy_(torch.cat([gathered[r, :, :sz] for r, sz in enumerate(sizes)], dim=1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        all_cols = host.numpy()
+        all_ruin = all_cols[6]
+        years_to_ruin = all_ruin / MONTHS_PER_YEAR
+        years_to_ruin[all_ruin < 0] = np.nan
+        self.last_d2h_bytes = n_global * 7 * 8 + (2 * T * nq + R * nw + 2 * k * T + R) * 8
         summary_df = pd.DataFrame({
             "Start Balance": all_cols[0],
             "Final Balance": all_cols[1],
-            "Success": all_succ,
-            "YearsToRuin": np.where(all_ruin < 0, np.nan, all_ruin.astype(np.float64) / MONTHS_PER_YEAR),
+            "Success": all_cols[5] != 0.0,
+            "YearsToRuin": years_to_ruin,
             "First Year Gross Withdrawal": all_cols[2],
             "First Year Real Gross Withdrawal": all_cols[3],
             "Inflation At Retirement": all_cols[4],
-        })
+        }, copy=False)
         s = samples.cpu().numpy()
         self._last_batch = b
         return (summary_df,

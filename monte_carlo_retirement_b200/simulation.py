@@ -431,6 +431,37 @@ class RetirementMonteCarloSimulator:
                 "succ": torch.empty(n, dtype=torch.uint8, pin_memory=True),
                 "ruin": torch.empty(n, dtype=torch.int32, pin_memory=True)}
 
+    # ---- hooks a sharded (multi-GPU) subclass overrides; identity on one GPU --------------------
+    def _shard(self, n_global: int) -> Tuple[int, int]:
+        """(offset, count) of the global path range this process owns."""
+        return 0, n_global
+
+    def _agree(self, flag: bool) -> bool:
+        """A decision every rank must take the same way."""
+        return bool(flag)
+
+    def _select(self, specs, out16, counts=None) -> None:
+        """Hook: all select rows of a step in one launch sequence (ShardedSimulator adds the all-reduce)."""
+        self.native_context.quantiles_rows(specs, out16, counts=counts)
+
+    def _band_quantiles(self, b: DeviceBatch, bands, real_bands, wr_bands, wr_counts) -> None:
+        """7-quantile nominal / real bands and 5-quantile NaN-skipping withdrawal-rate bands
+        (simulation.py:1045-1118) of a batch, as ONE multi-row select."""
+        import torch
+
+        ctx = self.native_context
+        T, R, n = b.T, b.R, b.n
+        nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
+        specs = (ctx.series_rows(b.traj, n, T, TRAJECTORY_QUANTILES) + ctx.series_rows(b.real, n, T, TRAJECTORY_QUANTILES)
+                 + ctx.series_rows(b.wr, n, R, WITHDRAWAL_RATE_QUANTILES))
+        out16 = torch.empty((2 * T + R, 16), dtype=torch.float64, device=b.cols.device)
+        cnt = torch.empty(2 * T + R, dtype=torch.int64, device=b.cols.device)
+        self._select(specs, out16, cnt)
+        bands.view(T, nq).copy_(out16[:T, :nq])
+        real_bands.view(T, nq).copy_(out16[T:2 * T, :nq])
+        wr_bands.view(R, nw).copy_(out16[2 * T:, :nw])
+        wr_counts.copy_(cnt[2 * T:])
+
     def _sample_columns(self, n: int) -> List[int]:
         """Columns DataFrame.sample(n=5, axis=1, random_state=main_seed) picks
         (simulation.py:1063-1072): RandomState(seed).choice(n, 5, replace=False)."""
@@ -477,9 +508,7 @@ class RetirementMonteCarloSimulator:
         samples = small[o:o + k * T]; o += k * T
         real_samples = small[o:o + k * T]
         wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-        ctx.quantiles(b.traj, n, n, T, TRAJECTORY_QUANTILES, bands)
-        ctx.quantiles(b.real, n, n, T, TRAJECTORY_QUANTILES, real_bands)
-        ctx.quantiles(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, wr_bands, counts=wr_counts)
+        self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
         ctx.gather_columns(b.traj, n, T, sample_cols, samples)
         ctx.gather_columns(b.real, n, T, sample_cols, real_samples)
         host_small = small.cpu()          # synchronises the main stream
@@ -531,16 +560,20 @@ class RetirementMonteCarloSimulator:
         import torch
 
         ctx = self.native_context
-        n = int(num_simulations)
+        n_global = int(num_simulations)
+        offset, n = self._shard(n_global)  # single GPU: (0, n_global)
         R0 = self.params_model.retirement_years
         series_bytes = 8 * n * (2 * self._trajectory_len(int(working_months)) + R0)
         free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
-        sweep = bool(bands) and (series_bytes > 0.6 * free_bytes or os.environ.get("MCR_SERIES_SWEEP") == "1")
+        sweep = self._agree(bool(bands) and (series_bytes > 0.6 * free_bytes
+                                             or os.environ.get("MCR_SERIES_SWEEP") == "1"))
         if timeline_events is not None:
             timeline_events[0].record()
-        b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=first_path)
+        part_first = first_path + offset
+        b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=part_first)
         if timeline_events is not None:
             timeline_events[1].record()
+        self._reduce_counts(b.counters)
         dev = b.cols.device
         T, R = b.T, b.R
         f64 = dict(dtype=torch.float64, device=dev)
@@ -550,25 +583,34 @@ class RetirementMonteCarloSimulator:
         # small = [swr, median start, median final(successful)] + final quantiles + 2 ranges
         small = torch.empty(3 + nf + 4, **f64)
         cnt = torch.empty(3, dtype=torch.int64, device=dev)
-        ctx.quantiles(rates, n, n, 1, [0.5], small[0:], counts=cnt[0:], median=True)
-        ctx.quantiles(b.cols[0], n, n, 1, [0.5], small[1:], counts=cnt[1:], median=True)
-        ctx.quantiles(b.cols[1], n, n, 1, [0.5], small[2:], counts=cnt[2:], mask=b.success, median=True)
-        ctx.quantiles(b.cols[1], n, n, 1, FINAL_BALANCE_QUANTILES, small[3:])
+        # every order statistic of the step in ONE multi-row select: 3 medians (different columns /
+        # cohorts), the 9 final-balance quantiles and, when the series are resident, the bands
+        specs = [(rates, n, None, [0.5], True), (b.cols[0], n, None, [0.5], True),
+                 (b.cols[1], n, b.success, [0.5], True), (b.cols[1], n, None, FINAL_BALANCE_QUANTILES, False)]
+        with_bands = bool(bands) and not sweep
+        if with_bands:
+            specs += (ctx.series_rows(b.traj, n, T, TRAJECTORY_QUANTILES) + ctx.series_rows(b.real, n, T, TRAJECTORY_QUANTILES)
+                      + ctx.series_rows(b.wr, n, R, WITHDRAWAL_RATE_QUANTILES))
+        desc = ctx.select_rows(specs)  # one descriptor per row (4 + 2T + R of them with the bands)
+        out16 = torch.empty((len(desc), 16), **f64)
+        cnt_all = torch.empty(len(desc), dtype=torch.int64, device=dev)
+        self._select(desc, out16, cnt_all)
+        small[0:3].copy_(out16[0:3, 0])
+        cnt.copy_(cnt_all[0:3])
+        small[3:3 + nf].copy_(out16[3, :nf])
         rng_m = small[3 + nf:3 + nf + 2]
         rng_1 = small[3 + nf + 2:3 + nf + 4]
         hists = torch.zeros(160, dtype=torch.int64, device=dev)
-        ctx.minmax(b.cols[1], n, rng_m, mask=b.success, divisor=1e6)
-        ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
-        ctx.minmax(b.cols[1], n, rng_1, mask=b.success, divisor=1.0)
-        ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
+        self._final_balance_histograms(b, rng_m, rng_1, hists)
         band_block = wr_counts = None
         if bands:
             band_block = torch.empty(2 * T * nq + R * nw, **f64)
             wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-            if not sweep:
-                ctx.quantiles(b.traj, n, n, T, TRAJECTORY_QUANTILES, band_block[0:])
-                ctx.quantiles(b.real, n, n, T, TRAJECTORY_QUANTILES, band_block[T * nq:])
-                ctx.quantiles(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, band_block[2 * T * nq:], counts=wr_counts)
+            if with_bands:
+                band_block[:T * nq].view(T, nq).copy_(out16[4:4 + T, :nq])
+                band_block[T * nq:2 * T * nq].view(T, nq).copy_(out16[4 + T:4 + 2 * T, :nq])
+                band_block[2 * T * nq:].view(R, nw).copy_(out16[4 + 2 * T:, :nw])
+                wr_counts.copy_(cnt_all[4 + 2 * T:])
             else:
                 # the three series do not fit together (e.g. 1.25e8 paths x 71 points = 71 GB each):
                 # recompute the batch once per series — Philox makes every (path, month) draw
@@ -576,14 +618,30 @@ class RetirementMonteCarloSimulator:
                 for which, rows, qs, off in (("traj", T, TRAJECTORY_QUANTILES, 0),
                                              ("real", T, TRAJECTORY_QUANTILES, T * nq),
                                              ("wr", R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)):
-                    part = self.run_batch_device(working_months, n, series=which, first_path=first_path)
-                    ctx.quantiles(getattr(part, which), n, n, rows, qs, band_block[off:],
-                                  counts=wr_counts if which == "wr" else None)
+                    part = self.run_batch_device(working_months, n, series=which, first_path=part_first)
+                    o16 = torch.empty((rows, 16), **f64)
+                    c16 = torch.empty(rows, dtype=torch.int64, device=dev)
+                    self._select(ctx.series_rows(getattr(part, which), n, rows, qs), o16, c16)
+                    band_block[off:off + rows * len(qs)].view(rows, len(qs)).copy_(o16[:, :len(qs)])
+                    if which == "wr":
+                        wr_counts.copy_(c16)
                     torch.cuda.current_stream().synchronize()  # release the series before the next one
                     del part
         self._last_batch = b
-        return DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
-                                wr_counts=wr_counts, rates=rates)
+        agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
+                               wr_counts=wr_counts, rates=rates)
+        agg.n_override = n_global
+        return agg
+
+    def _final_balance_histograms(self, b: DeviceBatch, rng_m, rng_1, hists) -> None:
+        """100-bin numpy histogram in $M (plotting.py:46-59) and the dashboard's 60-bin floor
+        histogram (HistogramChart.jsx:13-60) of the successful cohort's final balances."""
+        ctx = self.native_context
+        n = b.n
+        ctx.minmax(b.cols[1], n, rng_m, mask=b.success, divisor=1e6)
+        ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
+        ctx.minmax(b.cols[1], n, rng_1, mask=b.success, divisor=1.0)
+        ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
 
     def run_aggregates(self, working_months: int, num_simulations: int, *, bands: bool = True,
                        first_path: int = 0) -> Dict[str, Any]:

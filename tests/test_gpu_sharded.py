@@ -24,23 +24,22 @@ def _logical_distributed_quantiles(ctx, shards, rows, q, median=False, masks=Non
     """Drive mcr_select_step for several logical ranks; `all-reduce` = sum of their histograms."""
     import torch
 
+    lib = ctx.lib
+    import ctypes as C
+
     from monte_carlo_retirement_b200 import native
 
-    lib = ctx.lib
-    qs = (C.c_double * len(q))(*q)
-    flags = native.SEL_MEDIAN if median else 0
+    keep = [ctx.select_rows([(x[r], x.shape[-1], None if masks is None else masks[i], q, median) for r in range(rows)])
+            for i, x in enumerate(shards)]
+    descs = [C.cast(a.ctypes.data, C.POINTER(native.SelectRow)) for a in keep]
     st = [torch.empty(int(lib.mcr_select_state_bytes(rows)), dtype=torch.uint8, device="cuda") for _ in shards]
     hs = [torch.empty(int(lib.mcr_select_hist_bytes(rows)) // 4, dtype=torch.int32, device="cuda") for _ in shards]
-    outs = [torch.empty((rows, len(q)), dtype=torch.float64, device="cuda") for _ in shards]
+    outs = [torch.empty((rows, 16), dtype=torch.float64, device="cuda") for _ in shards]
     cnts = [torch.empty(rows, dtype=torch.int64, device="cuda") for _ in shards]
 
     def step(r, kind, p=0):
-        x = shards[r]
-        n = x.shape[-1]
-        m = None if masks is None else masks[r]
-        rc = lib.mcr_select_step(ctx.handle, kind, p, x.data_ptr(), n, n, rows, None if m is None else m.data_ptr(),
-                                 qs, len(q), flags, st[r].data_ptr(), hs[r].data_ptr(), outs[r].data_ptr(),
-                                 cnts[r].data_ptr(), None)
+        rc = lib.mcr_select_step(ctx.handle, kind, p, descs[r], rows, st[r].data_ptr(), hs[r].data_ptr(),
+                                 outs[r].data_ptr(), cnts[r].data_ptr(), None)
         assert rc == 0, lib.mcr_last_error(ctx.handle)
 
     for r in range(len(shards)):
@@ -58,7 +57,7 @@ def _logical_distributed_quantiles(ctx, shards, rows, q, median=False, masks=Non
             step(r, 2, p)
     for r in range(len(shards)):
         step(r, 3)
-    return outs, cnts
+    return [o[:, : len(q)].contiguous() for o in outs], cnts
 
 
 @pytest.mark.parametrize("splits", [(1000, 3000), (1, 4095, 2), (2048, 0, 2048)])

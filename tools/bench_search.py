@@ -37,9 +37,22 @@ def main():
     cfg_d = dict(getattr(scenarios, a.scenario), num_simulations_search=a.paths)
     cfg = Config(**cfg_d)
     R = cfg.retirement_years
-    res = {"scenario": a.scenario, "paths_per_candidate": a.paths, "policies": {}}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        from monte_carlo_retirement_b200.parallel import ShardedSimulator
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = {"scenario": a.scenario, "paths_per_candidate": a.paths, "n_gpus": world, "policies": {}}
     for pol in a.policies.split(","):
-        sim = RetirementMonteCarloSimulator(cfg, search_policy=pol)
+        if world > 1:
+            if pol == "sequential":
+                continue
+            sim = ShardedSimulator(cfg, device=local, search_policy=pol)
+        else:
+            sim = RetirementMonteCarloSimulator(cfg, search_policy=pol)
         sim.find_minimum_working_months(verbose=False)  # warm-up (context, allocator)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -49,14 +62,19 @@ def main():
         st = dict(sim.last_search_stats)
         probes = [p["working_months"] for p in curve]
         # the reference's decisions on the same table
-        table = dict(zip(sorted(set(probes)), sim.batched_success_counts(sorted(set(probes)), a.paths).cpu().tolist()))
+        table = dict(zip(sorted(set(probes)),
+                         sim._reduce_counts(sim.batched_success_counts(sorted(set(probes)), a.paths)).cpu().tolist()))
         m2, p2, c2, _ = orc.search_decisions(lambda m: table[m] / a.paths * 100.0, cfg.starting_working_months_search,
                                              cfg.target_probability, a.paths)
         assert (m2, p2, c2) == (months, prob, curve), "device search disagrees with the reference decision procedure"
         res["policies"][pol] = {"wall_s": dt, "months": months, "probability": prob, "probes": len(curve),
                                 "launches": st.get("launches"), "candidates_evaluated": st.get("candidates_evaluated"),
                                 "nominal_path_months_probed": sum((m + 12 * R) * a.paths for m in probes)}
-    print(json.dumps(res))
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
