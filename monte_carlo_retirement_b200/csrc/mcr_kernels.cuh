@@ -153,7 +153,8 @@ __global__ void k_helper(const __grid_constant__ DevParams P, int which, double 
 // +2 when the short exp polynomial is provably enough — native draws of the fast build only)
 static int pick_cfg(const DevParams& P, bool native_draws) {
   const int small = (MCR_FAST != 0 && native_draws && P.exp_small) ? 2 : 0;
-  if (P.taxed1 && P.taxed2 && !P.annual_any) return 1 + small;
+  // the both-taxed specialisation uses closed forms that need 1 - rate > eps
+  if (P.taxed1 && P.taxed2 && !P.annual_any && P.rate1 <= 0.999 && P.rate2 <= 0.999) return 1 + small;
   if (!P.taxed1 && !P.taxed2 && !P.annual_any) return 2 + small;
   return 0;
 }

@@ -83,6 +83,10 @@ struct Cfg {
   // Box-Muller normals of 32-bit uniforms are bounded by 6.77), so a degree-10 polynomial is
   // exact to < 3e-19 relative and no range test is needed. Native-RNG launches only.
   static constexpr bool kExpSmall = EXPSMALL != 0;
+  // kAlgebra: both assets taxed on realized gains with rate < 1 (checked by the launcher): the
+  // fast build may use the closed forms of the withdrawal pair and of the rebalance sale (see
+  // withdraw_pair_closed / rebalance_main).
+  static constexpr bool kAlgebra = TAXED1 == 1 && TAXED2 == 1 && ANNUAL == 0;
   static __device__ __forceinline__ bool taxed1(const DevParams& P) {
     if constexpr (TAXED1 < 0) return P.taxed1 != 0; else return TAXED1 != 0;
   }
@@ -351,7 +355,25 @@ __device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, d
   const double rate = sell1 ? (P.use1 ? P.rate1 : 0.0) : (P.use2 ? P.rate2 : 0.0);
   const double as = sell1 ? P.a1 : P.a2;
   double sale, fs;
-  if constexpr (FAST) {
+  if constexpr (FAST && C::kAlgebra && !FULL) {
+    // gf = gain/bs, den = 1 - as*gf*rate = (bs - as*gain*rate)/bs, so
+    //   fraction sold fs = sale/bs = drift/(bs - as*gain*rate)   (one reciprocal instead of two)
+    //   sale = fs*bs, basis removed = fs*cbs, taxable gain = fs*gain, purchase = sale - fs*gain*rate.
+    // den >= 1 - as*rate > eps because rate < 1, so the reference's max(eps, .) is inactive.
+    const double gr = pmax(0.0, bs - cbs) * rate;
+    fs = pmin(1.0, drift * Math<FAST>::rcp(bs - as * gr));
+    sale = fs * bs;
+    const double br_c = fs * cbs;
+    const double buy_c = sale - fs * gr;
+    double nbs = bs - sale, ncbs = cbs - br_c, nbo = bo + buy_c, ncbo = cbo + buy_c;
+    if (nbs <= kEps) { nbs = 0.0; ncbs = 0.0; }
+    if (nbo <= kEps) { nbo = 0.0; ncbo = 0.0; }
+    b1 = sell1 ? nbs : nbo;
+    cb1 = sell1 ? ncbs : ncbo;
+    b2 = sell1 ? nbo : nbs;
+    cb2 = sell1 ? ncbo : ncbs;
+    return;
+  } else if constexpr (FAST) {
     const double rb = Math<FAST>::rcp(bs);
     const double gf = pmax(0.0, bs - cbs) * rb;
     const double den = pmax(kEps, 1.0 - as * (gf * rate));
@@ -564,15 +586,45 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
         failed = true;
         break;
       }
-      const double cap1 = net_liq(b1, cb1, C::taxed1(P), P.rate1); // :726-737
-      const double cap2 = net_liq(b2, cb2, C::taxed2(P), P.rate2);
+      double cap1, cap2, tx1 = 0.0, tx2 = 0.0;
+      if constexpr (FAST && C::kAlgebra) {
+        tx1 = pmax(0.0, b1 - cb1) * P.rate1;   // tax due on full liquidation of each asset
+        tx2 = pmax(0.0, b2 - cb2) * P.rate2;
+        cap1 = b1 > kEps ? b1 - tx1 : 0.0;     // == net_liq()
+        cap2 = b2 > kEps ? b2 - tx2 : 0.0;
+      } else {
+        cap1 = net_liq(b1, cb1, C::taxed1(P), P.rate1); // :726-737
+        cap2 = net_liq(b2, cb2, C::taxed2(P), P.rate2);
+      }
       const double cap = cap1 + cap2;
       const double target = pmin(need, cap);   // :739-742 identity: max(0, .), need >= +0.0 and cap >= +0.0
       const double need_lo = need - kEps;
-      const double w1 = cap > kEps ? Math<FAST>::div(cap1, cap) : P.a1;   // :750-755
-      const double w2 = 1.0 - w1;
       double gw1, nw1, gw2, nw2;
-      withdraw_pair<FAST, C>(P, b1, cb1, target * w1, b2, cb2, target * w2, gw1, nw1, gw2, nw2);  // :757-777
+      bool closed = false;
+      if constexpr (FAST && C::kAlgebra) {
+        // Closed form of :750-777 when both assets really sell (b_i > eps, target > 0, cap > eps):
+        // the net target is split by w_i = cap_i/cap and grossed up by 1/(1 - gf_i*rate_i) =
+        // b_i/cap_i, so gross_i = target*b_i/cap = f*b_i with ONE fraction f = target/cap <= 1
+        // for both assets; then basis removed = f*cb_i, tax = f*tx_i, net cash = f*cap_i. One
+        // reciprocal instead of five; max(eps, 1 - etf) is inactive because rate < 1.
+        closed = b1 > kEps && b2 > kEps && cap > kEps && target > 0;
+        if (__builtin_expect(closed, 1)) {
+          const double f = pmin(1.0, target * Math<FAST>::rcp(cap));
+          gw1 = f * b1;
+          gw2 = f * b2;
+          nw1 = f * cap1;
+          nw2 = f * cap2;
+          double nb1 = b1 - gw1, ncb1 = cb1 - f * cb1, nb2 = b2 - gw2, ncb2 = cb2 - f * cb2;
+          if (nb1 <= kEps) { nb1 = 0.0; ncb1 = 0.0; }
+          if (nb2 <= kEps) { nb2 = 0.0; ncb2 = 0.0; }
+          b1 = nb1; cb1 = ncb1; b2 = nb2; cb2 = ncb2;
+        }
+      }
+      if (!closed) {
+        const double w1 = cap > kEps ? Math<FAST>::div(cap1, cap) : P.a1;   // :750-755
+        const double w2 = 1.0 - w1;
+        withdraw_pair<FAST, C>(P, b1, cb1, target * w1, b2, cb2, target * w2, gw1, nw1, gw2, nw2);  // :757-777
+      }
       yr_g1 += gw1;
       yr_g2 += gw2;
       yr_real += Math<FAST>::div((gw1 + gw2) * level_ret, pmax(level0, kEps));   // :778-782
