@@ -139,6 +139,7 @@ int validate_and_derive(const mcr_params& p, DevParams& d, double* live_start_ag
   d.taxed1 = d.use1 && d.rate1 > 0;
   d.taxed2 = d.use2 && d.rate2 > 0;
   d.growth_on = p.contribution_growth_rate_annual > 0;
+  d.algebra_ok = (d.taxed1 || d.taxed2) && (!d.taxed1 || d.rate1 <= 0.999) && (!d.taxed2 || d.rate2 <= 0.999);
   d.annual_any = (!d.use1 && d.ann1 > 0) || (!d.use2 && d.ann2 > 0);
   {
     // |mu/12| + sigma/sqrt(12) * z_max for the three factors; Box-Muller on 32-bit uniforms

@@ -45,6 +45,7 @@ struct DevParams {
   int32_t growth_on;       // contribution_growth_rate_annual > 0
   int32_t annual_any;      // some asset can owe annual tax (needs the P&L accumulators)
   int32_t R;               // retirement_years
+  int32_t algebra_ok;      // some realized-gains tax bites and every such rate is < 1: closed forms allowed
   int32_t exp_small;       // |monthly log-return| < 0.1 guaranteed for Philox normals (|z| <= 6.8)
   int32_t n_streams;       // streams with a positive amount, original order
   DevStream streams[MCR_MAX_STREAMS];
@@ -87,6 +88,10 @@ struct Cfg {
   // fast build may use the closed forms of the withdrawal pair and of the rebalance sale (see
   // withdraw_pair_closed / rebalance_main).
   static constexpr bool kAlgebra = TAXED1 == 1 && TAXED2 == 1 && ANNUAL == 0;
+  // generic configuration: the same closed forms behind a (warp-uniform) run-time test
+  static __device__ __forceinline__ bool algebra(const DevParams& P) {
+    if constexpr (TAXED1 < 0) return P.algebra_ok != 0; else return kAlgebra;
+  }
   static __device__ __forceinline__ bool taxed1(const DevParams& P) {
     if constexpr (TAXED1 < 0) return P.taxed1 != 0; else return TAXED1 != 0;
   }
@@ -355,7 +360,7 @@ __device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, d
   const double rate = sell1 ? (P.use1 ? P.rate1 : 0.0) : (P.use2 ? P.rate2 : 0.0);
   const double as = sell1 ? P.a1 : P.a2;
   double sale, fs;
-  if constexpr (FAST && C::kAlgebra && !FULL) {
+  if (FAST && !FULL && C::algebra(P)) {
     // gf = gain/bs, den = 1 - as*gf*rate = (bs - as*gain*rate)/bs, so
     //   fraction sold fs = sale/bs = drift/(bs - as*gain*rate)   (one reciprocal instead of two)
     //   sale = fs*bs, basis removed = fs*cbs, taxable gain = fs*gain, purchase = sale - fs*gain*rate.
@@ -373,7 +378,8 @@ __device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, d
     b2 = sell1 ? nbo : nbs;
     cb2 = sell1 ? ncbo : ncbs;
     return;
-  } else if constexpr (FAST) {
+  }
+  if constexpr (FAST) {
     const double rb = Math<FAST>::rcp(bs);
     const double gf = pmax(0.0, bs - cbs) * rb;
     const double den = pmax(kEps, 1.0 - as * (gf * rate));
@@ -587,9 +593,10 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
         break;
       }
       double cap1, cap2, tx1 = 0.0, tx2 = 0.0;
-      if constexpr (FAST && C::kAlgebra) {
-        tx1 = pmax(0.0, b1 - cb1) * P.rate1;   // tax due on full liquidation of each asset
-        tx2 = pmax(0.0, b2 - cb2) * P.rate2;
+      const bool algebra = FAST && C::algebra(P);
+      if (algebra) {
+        tx1 = C::taxed1(P) ? pmax(0.0, b1 - cb1) * P.rate1 : 0.0;   // tax due on full liquidation of each asset
+        tx2 = C::taxed2(P) ? pmax(0.0, b2 - cb2) * P.rate2 : 0.0;
         cap1 = b1 > kEps ? b1 - tx1 : 0.0;     // == net_liq()
         cap2 = b2 > kEps ? b2 - tx2 : 0.0;
       } else {
@@ -601,7 +608,7 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
       const double need_lo = need - kEps;
       double gw1, nw1, gw2, nw2;
       bool closed = false;
-      if constexpr (FAST && C::kAlgebra) {
+      if (algebra) {
         // Closed form of :750-777 when both assets really sell (b_i > eps, target > 0, cap > eps):
         // the net target is split by w_i = cap_i/cap and grossed up by 1/(1 - gf_i*rate_i) =
         // b_i/cap_i, so gross_i = target*b_i/cap = f*b_i with ONE fraction f = target/cap <= 1
