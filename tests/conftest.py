@@ -16,6 +16,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # the suites bind the in-tree engine library: (re)build it when it is missing or stale (nvcc
+    # cross-compiles sm_100a without a GPU) and the CPU oracle next to it
+    from monte_carlo_retirement_b200 import build as mcr_build
+
+    if mcr_build.needs_build():
+        mcr_build.build()
+    from oracle import oracle as orc
+
+    orc.build()
 
 
 def pytest_collection_modifyitems(config, items):
