@@ -545,6 +545,8 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
   double lockn[MCR_MAX_STREAMS];
   uint32_t lockn_mask = 0;
   const int ns = P.n_streams;
+  double idx_coeff = 0.0, fixed_income = 0.0;  // fast build: cached stream sums
+  int next_event = 0;                          // next retirement month at which they change
   double fy_gross = 0.0, fy_real = 0.0;
   bool ok = !pre_fail;                                             // :627-629
   int ruin = pre_fail ? 0 : -1;
@@ -561,14 +563,40 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
       const double level0 = level;                                 // :644-647
       const double need_nominal = P.E * level0;
       double income = 0.0;                                         // :649-677
-      if (ns > 0) stream_income(P.streams[0], window[0], window[1], r, level0, lock0, locked0, income);
-      if (ns > 1) stream_income(P.streams[1], window[2], window[3], r, level0, lock1, locked1, income);
-      for (int k = 2; k < ns; ++k) {
-        bool lk = (lockn_mask >> k) & 1u;
-        double lv = lk ? lockn[k] : 0.0;
-        const bool was = lk;
-        stream_income(P.streams[k], window[2 * k], window[2 * k + 1], r, level0, lv, lk, income);
-        if (lk && !was) { lockn[k] = lv; lockn_mask |= 1u << k; }
+      if constexpr (FAST) {
+        // The set of paying streams changes only at window boundaries (warp-uniform months):
+        // between two boundaries net income = level * sum(indexed amount*(1-tax)) + sum(locked
+        // nominal*(1-tax)), one DFMA per month. The sums are rebuilt at a boundary month.
+        if (__builtin_expect(r == next_event, 0)) {
+          idx_coeff = 0.0;
+          fixed_income = 0.0;
+          int nxt_ev = 0x7fffffff;
+          for (int k = 0; k < ns; ++k) {
+            const int first = window[2 * k], end = window[2 * k + 1];
+            if (first > r && first < nxt_ev) nxt_ev = first;
+            if (end > r && end < nxt_ev) nxt_ev = end;
+            if (r >= first && r < end) {
+              if (P.streams[k].indexed) {
+                idx_coeff += P.streams[k].amount * P.streams[k].net_factor;
+              } else {
+                if (!((lockn_mask >> k) & 1u)) { lockn[k] = P.streams[k].amount * level0; lockn_mask |= 1u << k; }
+                fixed_income += lockn[k] * P.streams[k].net_factor;
+              }
+            }
+          }
+          next_event = nxt_ev;
+        }
+        income = idx_coeff * level0 + fixed_income;
+      } else {
+        if (ns > 0) stream_income(P.streams[0], window[0], window[1], r, level0, lock0, locked0, income);
+        if (ns > 1) stream_income(P.streams[1], window[2], window[3], r, level0, lock1, locked1, income);
+        for (int k = 2; k < ns; ++k) {
+          bool lk = (lockn_mask >> k) & 1u;
+          double lv = lk ? lockn[k] : 0.0;
+          const bool was = lk;
+          stream_income(P.streams[k], window[2 * k], window[2 * k + 1], r, level0, lv, lk, income);
+          if (lk && !was) { lockn[k] = lv; lockn_mask |= 1u << k; }
+        }
       }
       const double need = pmax(0.0, need_nominal - income);        // :679-682
       const bool wants = need > kEps;
