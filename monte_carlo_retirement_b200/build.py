@@ -28,6 +28,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
 if os.environ.get("MCR_MIN_BLOCKS"):  # tuning experiments only
     COMMON += [f"-DMCR_MIN_BLOCKS={int(os.environ['MCR_MIN_BLOCKS'])}"]
+if os.environ.get("MCR_BLOCK"):
+    COMMON += [f"-DMCR_BLOCK={int(os.environ['MCR_BLOCK'])}"]
 UNITS = [
     ("mcr_kernels_strict.cu", ["-fmad=false"]),
     ("mcr_kernels_fast.cu", ["-fmad=true"]),

@@ -8,7 +8,10 @@
 
 namespace mcr {
 
-constexpr int kBlock = 128;  // 4 warps per CTA
+#ifndef MCR_BLOCK
+#define MCR_BLOCK 128
+#endif
+constexpr int kBlock = MCR_BLOCK;  // threads per CTA
 #ifndef MCR_MIN_BLOCKS
 #define MCR_MIN_BLOCKS 6     // resident CTAs per SM the register allocator must leave room for (80 regs)
 #endif
