@@ -126,6 +126,9 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         self.native_context.quantiles_rows(specs, out16, counts=counts, all_reduce=self.coll.sum_,
                                            all_reduce_min=self.coll.min_)
 
+    def _reduce_samples(self, block):
+        return self.coll.sum_(block)
+
     def _final_balance_histograms(self, b, rng_m, rng_1, hists) -> None:
         import torch
 
@@ -148,7 +151,6 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def run_monte_carlo_simulations(self, working_months: int, num_simulations: int):
         import torch
 
-        ctx = self.native_context
         coll = self.coll
         n_global = int(num_simulations)
         lo, n = shard_range(n_global, coll.rank, coll.world)
@@ -163,17 +165,11 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
         self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)  # one distributed multi-row select
         # sample paths: each rank contributes the columns it owns, summed into a zero block
-        cols = self._sample_columns(n_global)
-        k = len(cols)
+        k = len(self._sample_columns(n_global))
         samples = torch.zeros((2, k, T), **f64)
-        mine = [(j, c - lo) for j, c in enumerate(cols) if lo <= c < lo + n]
-        if mine:
-            tmp = torch.empty((len(mine), T), **f64)
-            ctx.gather_columns(b.traj, n, T, [c for _, c in mine], tmp)
-            samples[0, [j for j, _ in mine]] = tmp
-            ctx.gather_columns(b.real, n, T, [c for _, c in mine], tmp)
-            samples[1, [j for j, _ in mine]] = tmp
-        coll.sum_(samples)
+        self._gather_samples(b.traj, n, T, lo, n_global, samples[0])
+        self._gather_samples(b.real, n, T, lo, n_global, samples[1])
+        self._reduce_samples(samples)
         # summary columns of all shards, in global path order: ONE all-gather of a packed
         # [5 f64 | success | ruin] block per rank over NVLink, one pinned D2H, zero-copy DataFrame
         sizes = [shard_range(n_global, r, coll.world)[1] for r in range(coll.world)]

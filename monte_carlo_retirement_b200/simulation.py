@@ -192,6 +192,10 @@ class DeviceAggregates:
             out["withdrawal_rate_bands"] = pd.DataFrame(blk[2 * T * nq:].reshape(R, nw).copy(),
                                                         columns=WITHDRAWAL_RATE_QUANTILES)
             out["withdrawal_rate_counts"] = [int(v) for v in self.wr_counts.cpu().numpy()]
+        if getattr(self, "sample_block", None) is not None:
+            smp = self.sample_block.cpu().numpy()
+            out["sample_paths"] = smp[0].tolist()
+            out["real_sample_paths"] = smp[1].tolist()
         n_success = int(counters[0])
         out.update({
             "num_simulations": n,
@@ -471,6 +475,26 @@ class RetirementMonteCarloSimulator:
             self._sample_column_cache[n] = [int(c) for c in cols]
         return self._sample_column_cache[n]
 
+    def _reduce_samples(self, block):
+        """Hook for multi-GPU sharding: every rank fills the sample rows it owns, the rest stay zero."""
+        return block
+
+    def _gather_samples(self, series, n_local: int, T: int, first: int, n_global: int, out) -> None:
+        """Copy the sampled global columns this process owns from a time-major [T][n_local] series
+        into the rows of `out` ([k, T], zero-initialised)."""
+        import torch
+
+        mine = [(j, c - first) for j, c in enumerate(self._sample_columns(n_global)) if first <= c < first + n_local]
+        if not mine:
+            return
+        rows = [j for j, _ in mine]
+        if rows == list(range(out.shape[0])):
+            self.native_context.gather_columns(series, n_local, T, [c for _, c in mine], out)
+        else:
+            tmp = torch.empty((len(mine), T), dtype=torch.float64, device=out.device)
+            self.native_context.gather_columns(series, n_local, T, [c for _, c in mine], tmp)
+            out[rows] = tmp
+
     def run_monte_carlo_simulations(self, working_months: int, num_simulations: int):
         """simulation.py:952-1128 — returns (summary_df, traj_pct_df, samples, wr_pct_df,
         real_pct_df, real_samples, wr_counts)."""
@@ -552,11 +576,13 @@ class RetirementMonteCarloSimulator:
 
     # ---- aggregate-only mode: nothing N-sized leaves the device ----------
     def aggregates_device(self, working_months: int, num_simulations: int, *, bands: bool = True,
-                          first_path: int = 0, timeline_events=None) -> "DeviceAggregates":
+                          first_path: int = 0, timeline_events=None, samples: bool = False) -> "DeviceAggregates":
         """Enqueue one batch and every device-side reduction the callers make over summary_df
         (server.py:439-461,525-532; main.py:112-133; utils.py:97-102; plotting.py:46-59;
         HistogramChart.jsx:13-60). Nothing is copied to the host and nothing synchronises.
-        `timeline_events=(start, end)` records CUDA events around the timeline kernel."""
+        `timeline_events=(start, end)` records CUDA events around the timeline kernel;
+        `samples=True` (with bands) also keeps the 5 sampled nominal / real paths of
+        simulation.py:1063-1078 — 2 x 5 x T values, the only per-path data the payload needs."""
         import torch
 
         ctx = self.native_context
@@ -602,11 +628,16 @@ class RetirementMonteCarloSimulator:
         rng_1 = small[3 + nf + 2:3 + nf + 4]
         hists = torch.zeros(160, dtype=torch.int64, device=dev)
         self._final_balance_histograms(b, rng_m, rng_1, hists)
-        band_block = wr_counts = None
+        band_block = wr_counts = sample_block = None
+        if bands and samples:
+            sample_block = torch.zeros((2, len(self._sample_columns(n_global)), T), **f64)
         if bands:
             band_block = torch.empty(2 * T * nq + R * nw, **f64)
             wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
             if with_bands:
+                if sample_block is not None:
+                    self._gather_samples(b.traj, n, T, offset, n_global, sample_block[0])
+                    self._gather_samples(b.real, n, T, offset, n_global, sample_block[1])
                 band_block[:T * nq].view(T, nq).copy_(out16[4:4 + T, :nq])
                 band_block[T * nq:2 * T * nq].view(T, nq).copy_(out16[4 + T:4 + 2 * T, :nq])
                 band_block[2 * T * nq:].view(R, nw).copy_(out16[4 + 2 * T:, :nw])
@@ -625,11 +656,16 @@ class RetirementMonteCarloSimulator:
                     band_block[off:off + rows * len(qs)].view(rows, len(qs)).copy_(o16[:, :len(qs)])
                     if which == "wr":
                         wr_counts.copy_(c16)
+                    elif sample_block is not None:
+                        self._gather_samples(getattr(part, which), n, T, offset, n_global,
+                                             sample_block[0 if which == "traj" else 1])
                     torch.cuda.current_stream().synchronize()  # release the series before the next one
                     del part
         self._last_batch = b
+        if sample_block is not None:
+            self._reduce_samples(sample_block)
         agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
-                               wr_counts=wr_counts, rates=rates)
+                               wr_counts=wr_counts, rates=rates, sample_block=sample_block)
         agg.n_override = n_global
         return agg
 
@@ -644,9 +680,10 @@ class RetirementMonteCarloSimulator:
         ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
 
     def run_aggregates(self, working_months: int, num_simulations: int, *, bands: bool = True,
-                       first_path: int = 0) -> Dict[str, Any]:
+                       first_path: int = 0, samples: bool = False) -> Dict[str, Any]:
         """aggregates_device(...) copied to the host as a dict (a few KB)."""
-        return self.aggregates_device(working_months, num_simulations, bands=bands, first_path=first_path).to_host()
+        return self.aggregates_device(working_months, num_simulations, bands=bands, first_path=first_path,
+                                      samples=samples).to_host()
 
     # ---- batched search ------------------------------------------------------------------------
     def batched_success_counts(self, candidates: Sequence[int], num_simulations: int, *, first_path: int = 0,
