@@ -41,20 +41,22 @@ __device__ __forceinline__ double value_of(uint64_t k) {
 // (rows x 16 K-element chunks, every requested quantile of a row resolved in the same scan,
 // merged into hist[row]) + one small "advance" step that walks each target's bucket to the
 // digit holding its rank. Two things keep the number of FULL scans of a row at 3-4:
-//   * adaptive start: pass 0 also reduces the row's min/max key; all keys share the leading
-//     clz(min ^ max) bits, so those are resolved for free and the 8-bit digits of the following
-//     passes start at the first bit that actually discriminates. A constant row is finished
-//     after pass 0; a tightly concentrated row (early accumulation years) is as cheap as a
-//     wide one;
-//   * collect + tail: after three passes a fourth scan gathers the few elements that still
-//     share a target's prefix into a per-row candidate list; one more kernel sorts that list in
-//     shared memory, reads every target off it and interpolates. A bucket that overflows the
-//     list but holds ONE repeated value (zero-padded failed paths) is recognised by its
-//     min == max; only an overflowing bucket of distinct values falls back to scanning the row.
+//   * adaptive start: pass 0 only counts the valid elements and reduces the row's min/max key;
+//     all keys share the leading clz(min ^ max) bits, so those are resolved for free and the
+//     8-bit digits of the following passes start at the first bit that actually discriminates.
+//     A constant row is finished after pass 0; a tightly concentrated row (early accumulation
+//     years) is as cheap as a wide one;
+//   * collect + tail: as soon as the live buckets of a row fit its candidate list together
+//     (typically after two digit passes; three when zero-padded failures stretch the key
+//     range) the row stops scanning; one more scan gathers the elements that share a target's
+//     prefix into the list; one more kernel sorts that list in shared memory, reads every
+//     target off it and interpolates. A bucket that stays too big for the list but holds ONE
+//     repeated value (zero-padded failed paths) is recognised by its min == max; only a big
+//     bucket of distinct values after all full passes falls back to scanning the row.
 // The per-pass split also lets a multi-GPU caller all-reduce hist[] between the two halves of
-// a pass and obtain exact GLOBAL order statistics without moving data; that
-// stepwise protocol uses fixed 8-bit digits (adaptive = 0), since min/max would need their own
-// all-reduce.
+// a pass and obtain exact GLOBAL order statistics without moving data; the row
+// extremes then take one all-reduce(MIN) of their own (k_sel_extremes), without which that
+// stepwise protocol falls back to fixed 8-bit digits from bit 0 (adaptive = 0).
 // Layout: hist[rows][kMaxTargets][256] u32 is its own contiguous array (the all-reduced
 // buffer); the rest of the state is SelRow[rows] followed by the candidate lists.
 struct SelRow {
@@ -77,14 +79,14 @@ struct SelRow {
   int32_t collected;                // candidate list is valid
   int32_t adaptive;                 // row extremes are available after pass 0
   int32_t fused;                    // single-GPU call: k_sel_tail finishes the row (ungathered buckets allowed)
-  int32_t pad_;
+  int32_t ready;                    // every live bucket fits the candidate list: no more full scans needed
 };
 
 constexpr int kHistThreads = 256;
 constexpr int kChunk = 16384;       // elements of one row handled by one CTA
 constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
 constexpr int kBigBucket = 2048;    // buckets above this are not gathered (resolved by min == max, else by scanning)
-constexpr int kFullPasses = 3;      // passes that scan the rows before the collect
+constexpr int kFullPasses = 4;      // passes that may scan the rows before the collect (pass 0 + up to 3 digits)
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 
 __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, const RowDesc* __restrict__ desc,
@@ -95,26 +97,54 @@ __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ his
   for (int k = threadIdx.x; k < kHistWords; k += blockDim.x) H[k] = 0;
   if (threadIdx.x == 0) {
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
-    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused;
+    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused; R.ready = 0;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
 
-// membership of a key's resolved-bits part among the live prefixes: a 256-entry table on the
-// low byte of the prefix (the most discriminating one) with chaining, instead of a binary search
+// ---- scan machinery ---------------------------------------------------------------------------
+// The scans are instruction-issue bound before they are HBM bound (ncu, r01h: 77 warp
+// instructions per element in the first version), so everything per-element is kept to 32-bit
+// integer work on the two halves of the key, the pass geometry lives in registers (Probe), the
+// shared-memory tables are addressed through precomputed 32-bit shared-window addresses, and the
+// loop over a chunk has a branch-free body for full tiles.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds_u64(uint32_t a, uint32_t& lo, uint32_t& hi) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// order-preserving key as two 32-bit halves (3 integer instructions)
+__device__ __forceinline__ void key_halves(double v, uint32_t& hi, uint32_t& lo) {
+  lo = (uint32_t)__double2loint(v);
+  hi = (uint32_t)__double2hiint(v);
+  const uint32_t s = (uint32_t)((int32_t)hi >> 31);
+  lo ^= s;
+  hi ^= s | 0x80000000u;
+}
+
+// membership of a key among the live prefixes: LEFT-ALIGNED prefixes in a 256-entry chained
+// table keyed by the last resolved byte (the most discriminating one)
 struct PrefixTable {
-  uint64_t up[kMaxTargets];
+  uint64_t up[kMaxTargets];   // prefix << (64 - rb)
   uint8_t head[256];          // group + 1, 0 == none
   uint8_t next[kMaxTargets];  // chain
 };
 
-__device__ __forceinline__ void build_table(PrefixTable& T, const SelRow& R, int ng) {
+__device__ __forceinline__ void build_table(PrefixTable& T, const SelRow& R, int ng, int rb) {
   for (int k = threadIdx.x; k < 256; k += blockDim.x) T.head[k] = 0;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int g = 0; g < ng; ++g) {
       const uint64_t u = R.uprefix[g];
-      T.up[g] = u;
+      T.up[g] = u << (64 - rb);
       T.next[g] = T.head[u & 255u];
       T.head[u & 255u] = (uint8_t)(g + 1);
     }
@@ -122,100 +152,201 @@ __device__ __forceinline__ void build_table(PrefixTable& T, const SelRow& R, int
   __syncthreads();
 }
 
-__device__ __forceinline__ int lookup(const PrefixTable& T, uint64_t hi) {
-  int g = T.head[hi & 255u];
+// geometry of the current pass over one row, uniform across the CTA
+struct Probe {
+  uint32_t m_hi, m_lo;   // mask of the rb resolved (leading) key bits
+  uint32_t p_hi, p_lo;   // group 0's left-aligned prefix (single-group fast path)
+  int pshift;            // 64 - rb        : key >> pshift == prefix
+  int dshift;            // 64 - rb - w    : position of the digit being histogrammed
+  uint32_t dmask;
+  uint32_t a_head, a_up, a_next, a_hist;  // shared-window addresses
+};
+
+__device__ __forceinline__ Probe make_probe(const SelRow& R, int rb, int w, const PrefixTable& T, const uint32_t* sh) {
+  Probe P;
+  const uint64_t m = rb == 0 ? 0ull : (~0ull << (64 - rb));
+  const uint64_t p0 = rb == 0 ? 0ull : (R.uprefix[0] << (64 - rb));
+  P.m_hi = (uint32_t)(m >> 32); P.m_lo = (uint32_t)m;
+  P.p_hi = (uint32_t)(p0 >> 32); P.p_lo = (uint32_t)p0;
+  P.pshift = 64 - rb;
+  P.dshift = 64 - rb - w;
+  P.dmask = (1u << w) - 1u;
+  P.a_head = smem_addr(T.head); P.a_up = smem_addr(T.up); P.a_next = smem_addr(T.next);
+  P.a_hist = smem_addr(sh);
+  return P;
+}
+
+enum ScanMode { kScanTop = 1, kScanOne = 2, kScanTable = 3 };  // rb == 0 | one live prefix | several
+
+template <int MODE>
+__device__ __forceinline__ int group_of(const Probe& P, uint32_t hi, uint32_t lo) {
+  if (MODE == kScanTop) return 0;
+  if (MODE == kScanOne) return (((hi ^ P.p_hi) & P.m_hi) | ((lo ^ P.p_lo) & P.m_lo)) == 0u ? 0 : -1;
+  const uint64_t k = ((uint64_t)hi << 32) | lo;
+  uint32_t g = lds_u8(P.a_head + ((uint32_t)(k >> P.pshift) & 255u));
   while (g) {
-    if (T.up[g - 1] == hi) return g - 1;
-    g = T.next[g - 1];
+    uint32_t ulo, uhi;
+    lds_u64(P.a_up + (g - 1u) * 8u, ulo, uhi);
+    if ((((hi ^ uhi) & P.m_hi) | ((lo ^ ulo) & P.m_lo)) == 0u) return (int)g - 1;
+    g = lds_u8(P.a_next + g - 1u);
   }
   return -1;
 }
 
-// group of key k given `rb` resolved bits (-1: not in a live bucket)
-__device__ __forceinline__ int group_of(const PrefixTable& T, uint64_t k, int rb) {
-  return rb == 0 ? 0 : lookup(T, k >> (64 - rb));
-}
-
-// shared-memory histogram of the next digit (width w below the rb resolved bits) over
-// x[begin, stop) by the calling CTA (nthreads wide); optionally the running min/max key
-__device__ __forceinline__ void hist_scan(const double* __restrict__ x, const uint8_t* __restrict__ m, int64_t begin,
-                                          int64_t stop, int nthreads, int rb, int w, const PrefixTable& T, uint32_t* sh,
-                                          uint64_t* kmin, uint64_t* kmax) {
-  const int shift = 64 - rb - w;
-  const uint32_t dmask = (1u << w) - 1u;
-  uint64_t lo = ~0ull, hi = 0ull;
-  for (int64_t base = begin; base < stop; base += (int64_t)nthreads * 4) {
-    double v[4];
-    bool ok[4];
+// body(ok, v, hi, lo) for every element of x[0, cnt); all 32 lanes of a warp call it together
+// (the body may shuffle). Masked-out and NaN elements arrive with ok == false (pandas skips NaN).
+template <int NT, bool MASKED, typename Body>
+__device__ __forceinline__ void scan_elements(const double* __restrict__ x, const uint8_t* __restrict__ m, int cnt,
+                                              Body body) {
+  constexpr int U = 4;  // independent loads in flight per thread
+  const int tid = threadIdx.x;
+  int base = 0;
+  for (; base + U * NT <= cnt; base += U * NT) {  // full tiles: no bounds checks
+    double v[U];
+    bool ok[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // 4 independent loads in flight per thread
-      const int64_t e = base + (int64_t)u * nthreads + threadIdx.x;
-      ok[u] = e < stop && (!m || m[e]);
-      v[u] = ok[u] ? __ldcs(x + e) : 0.0;
+    for (int u = 0; u < U; ++u) {
+      const int e = base + u * NT + tid;
+      v[u] = __ldcs(x + e);
+      ok[u] = MASKED ? (m[e] != 0) : true;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int id = -1;
-      if (ok[u] && v[u] == v[u]) {  // NaN never takes part (pandas skips it)
-        const uint64_t k = key_of(v[u]);
-        lo = k < lo ? k : lo;
-        hi = k > hi ? k : hi;
-        const int g = group_of(T, k, rb);
-        if (g >= 0) id = g * 256 + (int)((uint32_t)(k >> shift) & dmask);
-      }
-      // concentrated data puts whole warps in one bin: one atomic for the warp in that case
-      const int id0 = __shfl_sync(0xffffffffu, id, 0);
-      if (__all_sync(0xffffffffu, id == id0)) {
-        if (id0 >= 0 && (threadIdx.x & 31) == 0) atomicAdd(&sh[id0], 32u);
-      } else if (id >= 0) {
-        atomicAdd(&sh[id], 1u);
-      }
+    for (int u = 0; u < U; ++u) {
+      uint32_t hi, lo;
+      key_halves(v[u], hi, lo);
+      body(ok[u] && v[u] == v[u], v[u], hi, lo);
     }
   }
-  if (kmin) {
+  for (; base < cnt; base += NT) {  // ragged end
+    const int e = base + tid;
+    bool ok = e < cnt;
+    if (MASKED) ok = ok && m[e] != 0;
+    const double v = ok ? __ldcs(x + e) : 0.0;
+    uint32_t hi, lo;
+    key_halves(v, hi, lo);
+    body(ok && v == v, v, hi, lo);
+  }
+}
+
+// shared-memory histogram of the next digit inside every live prefix bucket
+template <int NT, bool MASKED, int MODE>
+__device__ __forceinline__ void hist_elements(const Probe& P, const double* __restrict__ x,
+                                              const uint8_t* __restrict__ m, int cnt) {
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
+    int id = -1;
+    if (ok) {
+      const int g = group_of<MODE>(P, hi, lo);
+      const uint64_t k = ((uint64_t)hi << 32) | lo;
+      if (g >= 0) id = g * 256 + (int)((uint32_t)(k >> P.dshift) & P.dmask);
+    }
+    // concentrated data puts whole warps in one bin (and most keys of a late pass in none): one
+    // atomic — or none — for the warp in that case
+    const int id0 = __shfl_sync(0xffffffffu, id, 0);
+    if (__all_sync(0xffffffffu, id == id0)) {
+      if (id0 >= 0 && lane0) red_shared_add(P.a_hist + (uint32_t)id0 * 4u, 32u);
+    } else if (id >= 0) {
+      red_shared_add(P.a_hist + (uint32_t)id * 4u, 1u);
+    }
+  });
+}
+
+template <int NT>
+__device__ __forceinline__ void hist_dispatch(const Probe& P, const double* __restrict__ x, const uint8_t* __restrict__ m,
+                                              int cnt, int rb, int ng) {
+  if (rb == 0) {
+    if (m) hist_elements<NT, true, kScanTop>(P, x, m, cnt); else hist_elements<NT, false, kScanTop>(P, x, m, cnt);
+  } else if (ng == 1) {
+    if (m) hist_elements<NT, true, kScanOne>(P, x, m, cnt); else hist_elements<NT, false, kScanOne>(P, x, m, cnt);
+  } else {
+    if (m) hist_elements<NT, true, kScanTable>(P, x, m, cnt); else hist_elements<NT, false, kScanTable>(P, x, m, cnt);
+  }
+}
+
+// adaptive pass 0: no digit yet — count the valid elements and take the row's extreme keys
+template <int NT, bool MASKED>
+__device__ __forceinline__ void extremes_elements(const double* __restrict__ x, const uint8_t* __restrict__ m, int cnt,
+                                                  SelRow& R, uint32_t* H) {
+  uint64_t lo_k = ~0ull, hi_k = 0ull;
+  uint32_t n_ok = 0;
+  scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
+    const uint64_t k = ((uint64_t)hi << 32) | lo;
+    if (ok) {
+      ++n_ok;
+      lo_k = k < lo_k ? k : lo_k;
+      hi_k = k > hi_k ? k : hi_k;
+    }
+  });
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint64_t l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
-      lo = l2 < lo ? l2 : lo;
-      hi = h2 > hi ? h2 : hi;
-    }
-    if ((threadIdx.x & 31) == 0 && lo != ~0ull) {
-      atomicMin((unsigned long long*)kmin, (unsigned long long)lo);
-      atomicMax((unsigned long long*)kmax, (unsigned long long)hi);
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t l2 = __shfl_xor_sync(0xffffffffu, lo_k, o), h2 = __shfl_xor_sync(0xffffffffu, hi_k, o);
+    lo_k = l2 < lo_k ? l2 : lo_k;
+    hi_k = h2 > hi_k ? h2 : hi_k;
+    n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
+  }
+  if ((threadIdx.x & 31) == 0 && n_ok) {
+    atomicAdd(&H[0], n_ok);  // bin 0 of group 0 carries the count (summed like any histogram)
+    atomicMin((unsigned long long*)&R.kmin, (unsigned long long)lo_k);
+    atomicMax((unsigned long long*)&R.kmax, (unsigned long long)hi_k);
   }
 }
 
 // One pass, first half: histogram of the next digit inside every live prefix bucket. Rows that
-// are finished skip; rows with a valid candidate list scan that list (one CTA).
+// are finished or ready for the collect skip; rows with a valid candidate list scan that list
+// (one CTA).
 __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
                                                            const double* __restrict__ cand, int pass) {
   extern __shared__ uint32_t sh[];  // [n_groups][256]
   __shared__ PrefixTable T;
   SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
-  if (rb >= 64) return;
+  if (rb >= 64 || R.ready) return;
   const bool from_cand = R.collected && !R.overflow;
   if (from_cand && blockIdx.x > 0) return;
   const int64_t n = R.d.n;
   if (!from_cand && (int64_t)blockIdx.x * kChunk >= n) return;
-  const int ng = R.n_groups;
   uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
-  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
-  if (rb > 0) build_table(T, R, ng); else __syncthreads();
-  const double* __restrict__ x = from_cand ? cand + (size_t)blockIdx.y * kCandCap : R.d.x;
-  const uint8_t* __restrict__ m = from_cand ? nullptr : R.d.mask;
-  const int w = 64 - rb < 8 ? 64 - rb : 8;
   const int64_t begin = from_cand ? 0 : (int64_t)blockIdx.x * kChunk;
-  const int64_t stop = from_cand ? (int64_t)R.n_cand : (begin + kChunk < n ? begin + kChunk : n);
-  const bool want_minmax = pass == 0 && R.adaptive;
-  hist_scan(x, m, begin, stop, kHistThreads, rb, w, T, sh, want_minmax ? &R.kmin : nullptr, &R.kmax);
+  const int cnt = from_cand ? R.n_cand : (int)(begin + kChunk < n ? kChunk : n - begin);
+  const double* __restrict__ x = (from_cand ? cand + (size_t)blockIdx.y * kCandCap : R.d.x) + begin;
+  const uint8_t* __restrict__ m = (from_cand || !R.d.mask) ? nullptr : R.d.mask + begin;
+  if (pass == 0 && R.adaptive) {
+    if (m) extremes_elements<kHistThreads, true>(x, m, cnt, R, H); else extremes_elements<kHistThreads, false>(x, m, cnt, R, H);
+    return;
+  }
+  const int ng = R.n_groups;
+  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
+  if (rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
+  const int w = 64 - rb < 8 ? 64 - rb : 8;
+  const Probe P = make_probe(R, rb, w, T, sh);
+  hist_dispatch<kHistThreads>(P, x, m, cnt, rb, ng);
   __syncthreads();
   for (int k = threadIdx.x; k < ng * 256; k += kHistThreads)
     if (sh[k]) atomicAdd(&H[k], sh[k]);
 }
 
-// After kFullPasses passes: gather the elements that share a live prefix into the row's list.
+// After the full passes: gather the elements that share a live prefix into the row's list.
+template <bool MASKED, int MODE>
+__device__ __forceinline__ void collect_elements(const Probe& P, const double* __restrict__ x,
+                                                 const uint8_t* __restrict__ m, int cnt, SelRow& R,
+                                                 double* __restrict__ out, unsigned long long* s_min,
+                                                 unsigned long long* s_max, const int* s_big, int* s_full) {
+  scan_elements<kHistThreads, MASKED>(x, m, cnt, [&](bool ok, double v, uint32_t hi, uint32_t lo) {
+    if (!ok) return;
+    const int g = group_of<MODE>(P, hi, lo);
+    if (g < 0) return;
+    // bucket extremes (shared-memory atomics, merged once per CTA): a bucket of one repeated
+    // value is recognised later by min == max
+    const unsigned long long k = ((unsigned long long)hi << 32) | lo;
+    if (k < *(volatile unsigned long long*)&s_min[g]) atomicMin(&s_min[g], k);
+    if (k > *(volatile unsigned long long*)&s_max[g]) atomicMax(&s_max[g], k);
+    if (!s_big[g] && !*(volatile int*)s_full) {
+      const int at = atomicAdd(&R.n_cand, 1);
+      if (at < kCandCap) out[at] = v; else *s_full = 1;
+    }
+  });
+}
+
 __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand) {
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
@@ -226,44 +357,28 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
   if (rb >= 64 || R.collected) return;
   const int64_t n = R.d.n;
   if ((int64_t)blockIdx.x * kChunk >= n) return;
-  const uint8_t* __restrict__ mask = R.d.mask;
   const int ng = R.n_groups;
   if (threadIdx.x < kMaxTargets) {
     s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull;
     s_big[threadIdx.x] = threadIdx.x < ng ? R.gbig[threadIdx.x] : 0;
   }
   if (threadIdx.x == 0) s_full = 0;
-  build_table(T, R, ng);
-  const double* __restrict__ x = R.d.x;
-  double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
+  if (rb > 0) build_table(T, R, ng, rb); else __syncthreads();
   const int64_t begin = (int64_t)blockIdx.x * kChunk;
-  const int64_t stop = begin + kChunk < n ? begin + kChunk : n;
-  for (int64_t base = begin; base < stop; base += kHistThreads * 4) {
-    double v[4];
-    bool ok[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t e = base + u * kHistThreads + threadIdx.x;
-      ok[u] = e < stop && (!mask || mask[e]);
-      v[u] = ok[u] ? __ldcs(x + e) : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (ok[u] && v[u] == v[u]) {
-        const uint64_t k = key_of(v[u]);
-        const int g = group_of(T, k, rb);
-        if (g >= 0) {
-          // bucket extremes (shared-memory atomics, merged once per CTA): a bucket of one
-          // repeated value is recognised later by min == max
-          if (k < s_min[g]) atomicMin(&s_min[g], (unsigned long long)k);
-          if (k > s_max[g]) atomicMax(&s_max[g], (unsigned long long)k);
-          if (!s_big[g] && !s_full) {
-            const int at = atomicAdd(&R.n_cand, 1);
-            if (at < kCandCap) out[at] = v[u]; else s_full = 1;
-          }
-        }
-      }
-    }
+  const int cnt = (int)(begin + kChunk < n ? kChunk : n - begin);
+  const double* __restrict__ x = R.d.x + begin;
+  const uint8_t* __restrict__ m = R.d.mask ? R.d.mask + begin : nullptr;
+  double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
+  const Probe P = make_probe(R, rb, 0, T, nullptr);
+  if (rb == 0) {
+    if (m) collect_elements<true, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+    else collect_elements<false, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+  } else if (ng == 1) {
+    if (m) collect_elements<true, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+    else collect_elements<false, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+  } else {
+    if (m) collect_elements<true, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+    else collect_elements<false, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
   }
   __syncthreads();
   if (threadIdx.x < ng && s_min[threadIdx.x] != ~0ull) {
@@ -300,6 +415,7 @@ __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
       for (int g = 0; g < R.n_groups; ++g)
         if (R.gbig[g]) R.overflow = 1;
     R.collected = 1;
+    R.ready = 0;  // later (stepwise) passes histogram the candidate list
   }
 }
 
@@ -311,7 +427,9 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   const int lane = tid & 31, warp = tid >> 5;
   const int nq = spec.n_q, nt = 2 * nq;
   const int rb = R.rb;
-  if (rb < 64) {
+  // adaptive pass 0 only counted the valid elements (H[0]) and took the row's extreme keys
+  const bool counted_only = pass == 0 && R.adaptive;
+  if (rb < 64 && !R.ready) {
     if (pass == 0) {
       if (warp == 0) {
         int64_t part = 0;
@@ -363,7 +481,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
     // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
     // holding its rank
     const int w = 64 - rb < 8 ? 64 - rb : 8;
-    if (warp < nt && R.n_valid > 0) {
+    if (!counted_only && warp < nt && R.n_valid > 0) {
       const uint32_t* h = H + R.group[warp] * 256;
       uint32_t c[8];
       uint32_t local = 0;
@@ -396,28 +514,41 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
     __syncthreads();
     if (tid == 0) {
       int nrb = rb + w;
-      if (R.n_valid <= 0) nrb = 64;
-      if (pass == 0 && R.adaptive && R.n_valid > 0) {
-        // every key shares the leading clz(kmin ^ kmax) bits: resolve them for free (ranks do
-        // not change: all elements are in every target's bucket)
+      if (R.n_valid <= 0) {
+        nrb = 64;
+      } else if (counted_only) {
+        // every key shares the leading clz(kmin ^ kmax) bits: they are resolved for free, and all
+        // elements are in every target's bucket (ranks unchanged). A constant row is done.
         const uint64_t x = R.kmin ^ R.kmax;
         const int c = x ? __clzll((long long)x) : 64;
-        if (c > nrb) {
-          nrb = c;
-          for (int t = 0; t < nt; ++t) R.prefix[t] = c == 64 ? R.kmin : (R.kmin >> (64 - c));
+        nrb = c;
+        for (int t = 0; t < nt; ++t) {
+          R.prefix[t] = c == 0 ? 0ull : (c == 64 ? R.kmin : (R.kmin >> (64 - c)));
+          R.bcount[t] = R.n_valid;
         }
       }
       R.rb = nrb;
       // groups of the next pass (targets are rank-sorted, so prefixes are sorted)
+      int64_t gcount[kMaxTargets];
+      int64_t total = 0;
       int g = 0;
       for (int t = 0; t < nt; ++t) {
         if (t == 0 || R.prefix[t] != R.uprefix[g - 1]) {
-          R.gbig[g] = R.bcount[t] > kBigBucket;
+          gcount[g] = R.bcount[t];
+          total += R.bcount[t];
           R.uprefix[g++] = R.prefix[t];
         }
         R.group[t] = g - 1;
       }
       R.n_groups = g < 1 ? 1 : g;
+      // once the live buckets fit the candidate list together the row skips the remaining full
+      // scans; otherwise buckets above kBigBucket are left out of the gather (a bucket of one
+      // repeated value — zero-padded failed paths — never shrinks)
+      // (only where a tail kernel finishes the row from the gathered list: the plain stepwise
+      // protocol keeps histogramming, so it has no use for an early stop)
+      const bool ready = R.fused && nrb < 64 && total <= kCandCap;
+      for (int k = 0; k < g; ++k) R.gbig[k] = (!ready && gcount[k] > kBigBucket) ? 1 : 0;
+      R.ready = ready ? 1 : 0;
     }
   }
   for (int k = tid; k < kHistWords; k += blockDim.x) H[k] = 0;
@@ -503,7 +634,7 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
         } else {
           // candidates of this target = keys sharing its resolved prefix; they are contiguous
           // in the sorted list and its residual rank counts from the first of them
-          const uint64_t lo_key = R.prefix[tid] << (64 - rb);
+          const uint64_t lo_key = rb == 0 ? 0ull : (R.prefix[tid] << (64 - rb));
           int lo = 0, hi = nc;
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -517,12 +648,18 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
     } else {
       uint32_t* sh = (uint32_t*)s_keys;
       const double* __restrict__ x = R.d.x;
+      if (tid == 0) R.ready = 0;
+      __syncthreads();
       for (int pass = kFullPasses; R.rb < 64; ++pass) {
-        const int cur = R.rb;
+        const int cur = R.rb, ng = R.n_groups;
         const int w = 64 - cur < 8 ? 64 - cur : 8;
         for (int k = tid; k < kHistWords; k += kTailThreads) sh[k] = 0;
-        build_table(T, R, R.n_groups);
-        hist_scan(x, mask, 0, n, kTailThreads, cur, w, T, sh, nullptr, nullptr);
+        if (cur > 0 && ng > 1) build_table(T, R, ng, cur); else __syncthreads();
+        const Probe P = make_probe(R, cur, w, T, sh);
+        for (int64_t b0 = 0; b0 < n; b0 += (1 << 30)) {
+          const int cnt = (int)(n - b0 < (1 << 30) ? n - b0 : (1 << 30));
+          hist_dispatch<kTailThreads>(P, x + b0, mask ? mask + b0 : nullptr, cnt, cur, ng);
+        }
         __syncthreads();
         advance_row(R, sh, pass);
       }
