@@ -276,6 +276,23 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
  * once, concentrated rows need no extra scans). */
 #define MCR_SELECT_EXTREMES_GET 5
 #define MCR_SELECT_EXTREMES_SET 6
+/* Pooled tail (BEGIN with pass = 3: adaptive start + pooled tail). Rows stop scanning as soon as
+ * the GLOBAL histogram says their live buckets fit one candidate list; after
+ *   for pass in 0..mcr_select_full_passes()-1 { HIST ; [EXTREMES_*] ; all-reduce ; ADVANCE } ; COLLECT
+ * the ranks pool their few local candidates and every rank finishes all rows at once:
+ *   POOL_EXPORT ; all-reduce(SUM) counts region ; all-reduce(MIN) extremes region ;
+ *   POOL_PLACE  ; all-reduce(SUM) pool region   ; POOL_TAIL.
+ * For these three steps hist_dev is the exchange buffer — int64[mcr_select_exchange_words(n_rows,
+ * world)], regions at the word offsets mcr_select_exchange_layout() returns in at4 =
+ * {counts, extremes, pool, end} — and pass = rank | world << 8. POOL_TAIL writes the quantiles
+ * (layout as mcr_quantiles_rows) and leaves in word 0 of the buffer the number of rows it could
+ * NOT finish from the pool (a big bucket of distinct values; identical on all ranks): if that
+ * is not 0 the caller runs the plain stepwise protocol above instead. */
+#define MCR_SELECT_POOL_EXPORT 7
+#define MCR_SELECT_POOL_PLACE 8
+#define MCR_SELECT_POOL_TAIL 9
+int64_t mcr_select_exchange_words(int32_t rows, int32_t world);
+void mcr_select_exchange_layout(int32_t rows, int32_t world, int64_t* at4);
 int32_t mcr_select_full_passes(void);
 int64_t mcr_select_state_bytes(int32_t rows);
 int64_t mcr_select_hist_bytes(int32_t rows);

@@ -542,12 +542,18 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
 int64_t mcr_select_state_bytes(int32_t rows) { return (int64_t)quantile_state_bytes(rows); }
 int64_t mcr_select_hist_bytes(int32_t rows) { return (int64_t)quantile_hist_bytes(rows); }
 int32_t mcr_select_full_passes(void) { return select_full_passes(); }
+int64_t mcr_select_exchange_words(int32_t rows, int32_t world) { return (int64_t)select_exchange_words(rows, world); }
+void mcr_select_exchange_layout(int32_t rows, int32_t world, int64_t* at4) {
+  if (at4) select_exchange_layout(rows > 0 ? rows : 1, world > 0 ? world : 1, at4);
+}
 
 int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_row* rows_host, int32_t n_rows,
                     void* state_dev, void* hist_dev, double* out_dev, int64_t* counts_dev, void* stream) {
   if (!ctx || !state_dev || !hist_dev) return fail(ctx, MCR_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (pass < 0 || pass > 7) return fail(ctx, MCR_EINVAL, "bad pass");
+  const bool pooled_step = step >= MCR_SELECT_POOL_EXPORT && step <= MCR_SELECT_POOL_TAIL;
+  const int rank = pass & 0xff, world = (pass >> 8) & 0xff;  // POOL_* steps: pass = rank | world << 8
+  if (pooled_step ? (world < 1 || rank >= world) : (pass < 0 || pass > 7)) return fail(ctx, MCR_EINVAL, "bad pass");
   std::vector<RowDesc> d;
   if (int rc = make_descs(ctx, rows_host, n_rows, d)) return rc;
   int64_t max_n = 0;
@@ -561,7 +567,8 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
   cudaStream_t st = (cudaStream_t)stream;
   switch (step) {
     case MCR_SELECT_BEGIN:  // pass != 0: the caller will exchange the row extremes after HIST 0
-      MCR_CUDA(ctx, launch_sel_begin(n_rows, d.data(), state_dev, hist_dev, st, /*adaptive=*/pass != 0));
+      MCR_CUDA(ctx, launch_sel_begin(n_rows, d.data(), state_dev, hist_dev, st, /*adaptive=*/pass & 1,
+                                     /*fused=*/(pass >> 1) & 1));
       break;
     case MCR_SELECT_EXTREMES_GET:
     case MCR_SELECT_EXTREMES_SET:
@@ -577,6 +584,17 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
       break;
     case MCR_SELECT_ADVANCE:
       MCR_CUDA(ctx, launch_sel_advance(n_rows, max_nq, pass, state_dev, hist_dev, st));
+      break;
+    case MCR_SELECT_POOL_EXPORT:  // hist_dev is the exchange buffer for the POOL_* steps
+      MCR_CUDA(ctx, launch_sel_export(n_rows, state_dev, (long long*)hist_dev, rank, world, st));
+      break;
+    case MCR_SELECT_POOL_PLACE:
+      MCR_CUDA(ctx, launch_sel_place(n_rows, state_dev, (long long*)hist_dev, rank, world, st));
+      break;
+    case MCR_SELECT_POOL_TAIL:
+      if (!out_dev) return fail(ctx, MCR_EINVAL, "null output");
+      MCR_CUDA(ctx, launch_sel_tail_pooled(n_rows, state_dev, (long long*)hist_dev, world, out_dev, MCR_MAX_QUANTILES,
+                                           counts_dev, st));
       break;
     case MCR_SELECT_FINISH:
       if (!out_dev) return fail(ctx, MCR_EINVAL, "null output");

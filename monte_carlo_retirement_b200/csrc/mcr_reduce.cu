@@ -587,7 +587,8 @@ __device__ __forceinline__ double finish_value(const SelRow& R, int k) {
 constexpr int kTailThreads = 1024;
 __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ rows, const double* __restrict__ cand,
                                                            double* __restrict__ out, int out_stride,
-                                                           int64_t* __restrict__ counts) {
+                                                           int64_t* __restrict__ counts,
+                                                           long long* __restrict__ unresolved) {
   extern __shared__ uint64_t s_keys[];  // kCandCap keys (64 KB), reused as the histogram on the slow path
   __shared__ PrefixTable T;
   __shared__ int need_scan;
@@ -645,10 +646,14 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
         }
       }
       __syncthreads();
+    } else if (unresolved) {
+      // path shards on several GPUs: this rank only holds part of the row, so the row cannot be
+      // finished by scanning here — report it (the caller re-runs the stepwise protocol)
+      if (tid == 0) atomicAdd((unsigned long long*)unresolved, 1ull);
     } else {
       uint32_t* sh = (uint32_t*)s_keys;
       const double* __restrict__ x = R.d.x;
-      if (tid == 0) R.ready = 0;
+      if (tid == 0) { R.ready = 0; R.fused = 0; }  // no early stop from here on: every digit is walked
       __syncthreads();
       for (int pass = kFullPasses; R.rb < 64; ++pass) {
         const int cur = R.rb, ng = R.n_groups;
@@ -667,6 +672,74 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
   }
   if (tid < spec.n_q) out[(int64_t)blockIdx.x * out_stride + tid] = finish_value(R, tid);
   if (tid == 0 && counts) counts[blockIdx.x] = R.n_valid;
+}
+
+// ---- candidate exchange (path shards on several GPUs) -----------------------------------------
+// After the collect every rank holds the LOCAL elements of each live bucket; the buckets are
+// small by then (the rows stopped scanning because the GLOBAL histogram said they fit the
+// list), so instead of more all-reduced digit passes the ranks pool the candidates and each
+// finishes every row with the single-GPU tail. The exchange buffer is one int64 array
+//   xbuf = [ unresolved | counts[world][rows] | group extremes[rows][kMaxTargets][2] | pool[rows][kCandCap] ]
+// whose regions are combined by plain all-reduces: SUM of the counts (each rank fills only its
+// own line), MIN of the encoded extremes (as k_sel_extremes), SUM of the pool (each rank writes
+// its candidates, as bit patterns, at its own offset into zeros).
+__host__ __device__ inline size_t xbuf_counts_at() { return 1; }
+__host__ __device__ inline size_t xbuf_extremes_at(int rows, int world) { return 1 + (size_t)world * rows; }
+__host__ __device__ inline size_t xbuf_pool_at(int rows, int world) {
+  return xbuf_extremes_at(rows, world) + (size_t)rows * kMaxTargets * 2;
+}
+
+__global__ void k_sel_export(SelRow* __restrict__ rows, long long* __restrict__ xbuf, int n_rows, int rank, int world) {
+  const int r = blockIdx.x;
+  const SelRow& R = rows[r];
+  const unsigned long long top = 0x8000000000000000ull;
+  if (r == 0 && threadIdx.x == 0) xbuf[0] = 0;
+  for (int q = threadIdx.x; q < world; q += blockDim.x) {
+    long long c = 0;
+    if (q == rank && R.rb < 64) c = R.overflow ? (long long)kCandCap + 1 : (long long)R.n_cand;
+    xbuf[xbuf_counts_at() + (size_t)q * n_rows + r] = c;
+  }
+  long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * kMaxTargets * 2;
+  for (int g = threadIdx.x; g < kMaxTargets; g += blockDim.x) {
+    e[2 * g] = (long long)(R.gmin[g] ^ top);
+    e[2 * g + 1] = (long long)((~R.gmax[g]) ^ top);
+  }
+}
+
+__global__ void k_sel_place(SelRow* __restrict__ rows, const double* __restrict__ cand, long long* __restrict__ xbuf,
+                            int n_rows, int rank, int world) {
+  __shared__ long long s_off, s_total;
+  const int r = blockIdx.x;
+  SelRow& R = rows[r];
+  if (R.rb >= 64) return;
+  const unsigned long long top = 0x8000000000000000ull;
+  if (threadIdx.x == 0) {
+    long long off = 0, total = 0;
+    for (int q = 0; q < world; ++q) {
+      const long long c = xbuf[xbuf_counts_at() + (size_t)q * n_rows + r];
+      if (q < rank) off += c;
+      total += c;
+    }
+    s_off = off; s_total = total;
+  }
+  __syncthreads();
+  const long long total = s_total, off = s_off;
+  const int mine = R.n_cand;
+  long long* pool = xbuf + xbuf_pool_at(n_rows, world) + (size_t)r * kCandCap;
+  if (total <= kCandCap) {
+    const double* __restrict__ c = cand + (size_t)r * kCandCap;
+    for (int i = threadIdx.x; i < mine; i += blockDim.x) pool[off + i] = __double_as_longlong(c[i]);
+  }
+  const long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * kMaxTargets * 2;
+  __syncthreads();
+  if (threadIdx.x < kMaxTargets) {
+    R.gmin[threadIdx.x] = (unsigned long long)e[2 * threadIdx.x] ^ top;
+    R.gmax[threadIdx.x] = ~((unsigned long long)e[2 * threadIdx.x + 1] ^ top);
+  }
+  if (threadIdx.x == 0) {
+    R.overflow = total > kCandCap ? 1 : 0;
+    R.n_cand = total > kCandCap ? kCandCap : (int)total;
+  }
 }
 
 __global__ void k_sel_finish(const SelRow* __restrict__ rows, double* __restrict__ out, int out_stride,
@@ -888,12 +961,47 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
   e = cudaFuncSetAttribute(k_sel_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * kCandCap));
   if (e != cudaSuccess) return e;
   k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>((SelRow*)state, cand_of(state, rows), out,
-                                                                      out_stride, counts);
+                                                                      out_stride, counts, nullptr);
   ++*n_launches;
   return cudaGetLastError();
 }
 
 int select_full_passes() { return kFullPasses; }
+
+size_t select_exchange_words(int rows, int world) {
+  rows = rows > 0 ? rows : 1;
+  world = world > 0 ? world : 1;
+  return xbuf_pool_at(rows, world) + (size_t)rows * kCandCap;
+}
+void select_exchange_layout(int rows, int world, int64_t at[4]) {
+  at[0] = (int64_t)xbuf_counts_at();
+  at[1] = (int64_t)xbuf_extremes_at(rows, world);
+  at[2] = (int64_t)xbuf_pool_at(rows, world);
+  at[3] = (int64_t)select_exchange_words(rows, world);
+}
+
+cudaError_t launch_sel_export(int rows, void* state, long long* xbuf, int rank, int world, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(xbuf + xbuf_pool_at(rows, world), 0, sizeof(long long) * (size_t)rows * kCandCap, st);
+  if (e != cudaSuccess) return e;
+  k_sel_export<<<rows, 64, 0, st>>>((SelRow*)state, xbuf, rows, rank, world);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sel_place(int rows, void* state, long long* xbuf, int rank, int world, cudaStream_t st) {
+  if (rows > 0) k_sel_place<<<rows, 256, 0, st>>>((SelRow*)state, cand_of(state, rows), xbuf, rows, rank, world);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sel_tail_pooled(int rows, void* state, long long* xbuf, int world, double* out, int out_stride,
+                                   int64_t* counts, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(k_sel_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * kCandCap));
+  if (e != cudaSuccess) return e;
+  k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>(
+      (SelRow*)state, (const double*)(xbuf + xbuf_pool_at(rows, world)), out, out_stride, counts, xbuf);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_rates(const double* start, const double* fy_real, int64_t n, double* rates, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -32,6 +32,13 @@ cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, vo
 cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st);
 cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st);
 int select_full_passes();
+// pooled tail for path shards on several GPUs (see "candidate exchange" in mcr_reduce.cu)
+size_t select_exchange_words(int rows, int world);
+void select_exchange_layout(int rows, int world, int64_t at[4]);
+cudaError_t launch_sel_export(int rows, void* state, long long* xbuf, int rank, int world, cudaStream_t st);
+cudaError_t launch_sel_place(int rows, void* state, long long* xbuf, int rank, int world, cudaStream_t st);
+cudaError_t launch_sel_tail_pooled(int rows, void* state, long long* xbuf, int world, double* out, int out_stride,
+                                   int64_t* counts, cudaStream_t st);
 cudaError_t launch_sel_extremes(int rows, void* state, long long* ext, int store, cudaStream_t st);
 cudaError_t launch_sel_advance(int rows, int max_nq, int pass, void* state, void* hist, cudaStream_t st);
 cudaError_t launch_sel_finish(int rows, const void* state, double* out, int out_stride, int64_t* counts,

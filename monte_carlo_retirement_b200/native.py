@@ -140,6 +140,8 @@ SIGNATURES = {
     "mcr_select_state_bytes": (_I64, [_I32]),
     "mcr_select_hist_bytes": (_I64, [_I32]),
     "mcr_select_full_passes": (_I32, []),
+    "mcr_select_exchange_words": (_I64, [_I32, _I32]),
+    "mcr_select_exchange_layout": (None, [_I32, _I32, C.POINTER(_I64)]),
     "mcr_quantiles_rows": (C.c_int, [_VP, C.POINTER(SelectRow), _I32, _VP, _VP, _VP]),
     "mcr_select_step": (C.c_int, [_VP, _I32, _I32, C.POINTER(SelectRow), _I32, _VP, _VP, _VP, _VP, _VP]),
     "mcr_first_year_rates": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP]),
@@ -323,11 +325,13 @@ class Context:
         """Select spec for the rows of a time-major [rows, ld] series tensor."""
         return [(series[:rows], n, mask, q, median)]
 
-    def quantiles_rows(self, specs, out, counts=None, all_reduce=None, all_reduce_min=None) -> None:
+    def quantiles_rows(self, specs, out, counts=None, all_reduce=None, all_reduce_min=None, rank=None,
+                       world=None) -> None:
         """All rows of `specs` in one launch sequence; out is a [n_rows, 16] f64 device tensor.
-        With `all_reduce` (sums an int32 device tensor in place across ranks) the rows are this
+        With `all_reduce` (sums an integer device tensor in place across ranks) the rows are this
         rank's shards and every rank obtains the exact GLOBAL quantiles; `all_reduce_min`
-        (element-wise MIN of an int64 device tensor) additionally enables the adaptive start."""
+        (element-wise MIN of an int64 device tensor) additionally enables the adaptive start,
+        and with `rank` / `world` the pooled tail (mcr.h: MCR_SELECT_POOL_*)."""
         import torch
 
         arr_np = specs if hasattr(specs, "dtype") else self.select_rows(specs)
@@ -346,6 +350,37 @@ class Context:
 
         full = int(self.lib.mcr_select_full_passes())
         adaptive = all_reduce_min is not None
+        if adaptive and world is not None:
+            # pooled tail: `full` all-reduced passes at most, then the ranks pool their candidates
+            at4 = (_I64 * 4)()
+            self.lib.mcr_select_exchange_layout(n_rows, int(world), at4)
+            at = [int(v) for v in at4]
+            xbuf = torch.empty(int(at[3]), dtype=torch.int64, device=dev)
+            who = int(rank) | (int(world) << 8)
+
+            def pool_step(kind):
+                self._check(self.lib.mcr_select_step(self.handle, kind, who, arr, n_rows, _ptr(state), _ptr(xbuf),
+                                                     _ptr(out), _ptr(counts), _stream_handle()))
+
+            step(0, 3)
+            for p in range(full):
+                step(1, p)
+                if p == 0:
+                    ext = torch.empty((n_rows, 2), dtype=torch.int64, device=dev)
+                    step(5, 0, ext)
+                    all_reduce_min(ext)
+                    step(6, 0, ext)
+                all_reduce(hist)
+                step(2, p)
+            step(4)
+            pool_step(7)
+            all_reduce(xbuf[at[0]:at[1]])
+            all_reduce_min(xbuf[at[1]:at[2]])
+            pool_step(8)
+            all_reduce(xbuf[at[2]:at[3]])
+            pool_step(9)
+            if int(xbuf[0].item()) == 0:  # identical on every rank: all of them saw the same pool
+                return
         step(0, 1 if adaptive else 0)
         for p in range(8):
             if p == full:

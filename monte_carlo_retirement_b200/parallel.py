@@ -10,8 +10,9 @@ only aggregates couple them — so:
       - one all-reduce(sum) of the int64 counter block (success count, executed months,
         ruin-month histogram) and of the per-candidate success counts of the batched search;
       - min/max then histogram all-reduces for the final-balance histograms;
-      - the 8 x [rows x 32 x 256] int32 digit histograms of the distributed radix select, which
-        give EXACT global quantile bands without moving any per-path data;
+      - the <= 4 x [rows x 32 x 256] int32 digit histograms of the distributed radix select and one
+        pooled block of the few hundred candidates per row that are left after them, which give
+        EXACT global quantile bands without moving any per-path data;
       - (only when the caller asks for the reference's N-row summary_df) an all-gather of the
         7 summary columns.
 
@@ -124,7 +125,7 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def _select(self, specs, out16, counts=None) -> None:
         # exact GLOBAL order statistics: local digit histograms, all-reduced per pass
         self.native_context.quantiles_rows(specs, out16, counts=counts, all_reduce=self.coll.sum_,
-                                           all_reduce_min=self.coll.min_)
+                                           all_reduce_min=self.coll.min_, rank=self.coll.rank, world=self.coll.world)
 
     def _reduce_samples(self, block):
         return self.coll.sum_(block)
