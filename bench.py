@@ -226,6 +226,8 @@ def run_b200_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     native.load_library()
 

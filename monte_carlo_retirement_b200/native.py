@@ -326,12 +326,16 @@ class Context:
         return [(series[:rows], n, mask, q, median)]
 
     def quantiles_rows(self, specs, out, counts=None, all_reduce=None, all_reduce_min=None, rank=None,
-                       world=None) -> None:
+                       world=None, defer_check: bool = False):
         """All rows of `specs` in one launch sequence; out is a [n_rows, 16] f64 device tensor.
         With `all_reduce` (sums an integer device tensor in place across ranks) the rows are this
         rank's shards and every rank obtains the exact GLOBAL quantiles; `all_reduce_min`
         (element-wise MIN of an int64 device tensor) additionally enables the adaptive start,
-        and with `rank` / `world` the pooled tail (mcr.h: MCR_SELECT_POOL_*)."""
+        and with `rank` / `world` the pooled tail (mcr.h: MCR_SELECT_POOL_*). The pooled tail
+        reports rows it could not finish (rare: a big bucket of distinct values); by default
+        that count is read back here (one host sync) and the stepwise protocol re-run. With
+        `defer_check` the count is RETURNED as a 1-element device tensor instead and the caller
+        checks it at its next natural sync point (non-zero: call again without rank/world)."""
         import torch
 
         arr_np = specs if hasattr(specs, "dtype") else self.select_rows(specs)
@@ -339,7 +343,7 @@ class Context:
         arr = C.cast(arr_np.ctypes.data, C.POINTER(SelectRow))
         if all_reduce is None:
             self._check(self.lib.mcr_quantiles_rows(self.handle, arr, n_rows, _ptr(out), _ptr(counts), _stream_handle()))
-            return
+            return None
         dev = out.device
         state = torch.empty(int(self.lib.mcr_select_state_bytes(n_rows)), dtype=torch.uint8, device=dev)
         hist = torch.empty(int(self.lib.mcr_select_hist_bytes(n_rows)) // 4, dtype=torch.int32, device=dev)
@@ -379,8 +383,10 @@ class Context:
             pool_step(8)
             all_reduce(xbuf[at[2]:at[3]])
             pool_step(9)
+            if defer_check:
+                return xbuf[0:1].clone()
             if int(xbuf[0].item()) == 0:  # identical on every rank: all of them saw the same pool
-                return
+                return None
         step(0, 1 if adaptive else 0)
         for p in range(8):
             if p == full:
@@ -394,6 +400,7 @@ class Context:
             all_reduce(hist)
             step(2, p)
         step(3)
+        return None
 
     def quantiles_distributed(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, all_reduce,
                               counts=None, mask=None, median: bool = False) -> None:

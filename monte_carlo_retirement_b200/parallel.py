@@ -99,6 +99,10 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
                  **kw):
         super().__init__(params_model, main_seed_override, **kw)
         self.coll = collectives or Collectives()
+        self._agreed: Dict[Any, bool] = {}
+        self._select_flag = None
+        self._stepwise_only = False
+        self._sign4 = None
         if self.rng_mode != "philox":
             raise ValueError("sharding needs the counter-based Philox draws (rng='philox')")
 
@@ -116,16 +120,48 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def _shard(self, n_global: int) -> Tuple[int, int]:
         return shard_range(int(n_global), self.coll.rank, self.coll.world)
 
-    def _agree(self, flag: bool) -> bool:
+    def _agree(self, flag: bool, key=None) -> bool:
         import torch
 
+        if key is not None and key in self._agreed:
+            return self._agreed[key]
         t = torch.tensor([int(bool(flag))], dtype=torch.int32, device=self._torch_device())
-        return bool(self.coll.max_(t).item())
+        out = bool(self.coll.max_(t).item())
+        if key is not None:
+            self._agreed[key] = out
+        return out
 
     def _select(self, specs, out16, counts=None) -> None:
-        # exact GLOBAL order statistics: local digit histograms, all-reduced per pass
-        self.native_context.quantiles_rows(specs, out16, counts=counts, all_reduce=self.coll.sum_,
-                                           all_reduce_min=self.coll.min_, rank=self.coll.rank, world=self.coll.world)
+        # exact GLOBAL order statistics: local digit histograms all-reduced per pass, then the few
+        # candidates left are pooled across ranks (the "could not finish" count is checked at the
+        # caller's next host sync: _selects_ok)
+        ctx, coll = self.native_context, self.coll
+        if self._stepwise_only:
+            ctx.quantiles_rows(specs, out16, counts=counts, all_reduce=coll.sum_, all_reduce_min=coll.min_)
+            return
+        flag = ctx.quantiles_rows(specs, out16, counts=counts, all_reduce=coll.sum_, all_reduce_min=coll.min_,
+                                  rank=coll.rank, world=coll.world, defer_check=True)
+        if flag is not None:
+            import torch
+
+            self._select_flag = flag if self._select_flag is None else torch.maximum(self._select_flag, flag)
+
+    def _selects_ok(self) -> bool:
+        flag, self._select_flag = self._select_flag, None
+        return flag is None or int(flag.item()) == 0
+
+    def _stepwise_selects(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def forced():
+            before, self._stepwise_only = self._stepwise_only, True
+            try:
+                yield
+            finally:
+                self._stepwise_only = before
+
+        return forced()
 
     def _reduce_samples(self, block):
         return self.coll.sum_(block)
@@ -134,16 +170,18 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         import torch
 
         ctx, coll, n = self.native_context, self.coll, b.n
-        for rng, divisor in ((rng_m, 1e6), (rng_1, 1.0)):
-            ctx.minmax(b.cols[1], n, rng, mask=b.success, divisor=divisor)
-            # global range: NaN (empty local cohort) must not poison min/max
-            lo_v = torch.nan_to_num(rng[0:1], nan=float("inf"))
-            hi_v = torch.nan_to_num(rng[1:2], nan=float("-inf"))
-            coll.min_(lo_v)
-            coll.max_(hi_v)
-            empty = torch.isinf(lo_v)
-            rng[0:1] = torch.where(empty, torch.full_like(lo_v, float("nan")), lo_v)
-            rng[1:2] = torch.where(empty, torch.full_like(hi_v, float("nan")), hi_v)
+        ctx.minmax(b.cols[1], n, rng_m, mask=b.success, divisor=1e6)
+        ctx.minmax(b.cols[1], n, rng_1, mask=b.success, divisor=1.0)
+        # global ranges in ONE all-reduce(MIN) of [lo_m, -hi_m, lo_1, -hi_1]; NaN (empty local
+        # cohort) must not poison it
+        if self._sign4 is None:
+            self._sign4 = torch.tensor([1.0, -1.0, 1.0, -1.0], dtype=torch.float64, device=rng_m.device)
+        sign = self._sign4
+        packed = torch.nan_to_num(torch.cat([rng_m, rng_1]) * sign, nan=float("inf"))
+        coll.min_(packed)
+        packed = torch.where(torch.isinf(packed), float("nan"), packed * sign)
+        rng_m.copy_(packed[0:2])
+        rng_1.copy_(packed[2:4])
         ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
         ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
         coll.sum_(hists)
@@ -187,6 +225,9 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         else:
             host.copy_(torch.cat([gathered[r, :, :sz] for r, sz in enumerate(sizes)], dim=1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if not self._selects_ok():  # rare: the pooled select gave up on a row -> stepwise protocol
+            with self._stepwise_selects():
+                self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
         all_cols = host.numpy()
         all_ruin = all_cols[6]
         years_to_ruin = all_ruin / MONTHS_PER_YEAR

@@ -176,6 +176,16 @@ class DeviceAggregates:
         self.__dict__.update(kw)
 
     def to_host(self) -> Dict[str, Any]:
+        sim, args = getattr(self, "redo", (None, None))
+        if sim is not None:
+            import torch
+
+            torch.cuda.current_stream().synchronize()
+            if not sim._selects_ok():  # multi-GPU only, rare: a select shortcut gave up on a row
+                with sim._stepwise_selects():
+                    again = sim.aggregates_device(**args)
+                again.redo = (None, None)
+                return again.to_host()
         b = self.batch
         n, T, R = int(getattr(self, "n_override", b.n)), b.T, b.R
         nq, nw, nf = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES), len(FINAL_BALANCE_QUANTILES)
@@ -440,9 +450,19 @@ class RetirementMonteCarloSimulator:
         """(offset, count) of the global path range this process owns."""
         return 0, n_global
 
-    def _agree(self, flag: bool) -> bool:
-        """A decision every rank must take the same way."""
+    def _agree(self, flag: bool, key=None) -> bool:
+        """A decision every rank must take the same way (`key`: remember it for this call shape)."""
         return bool(flag)
+
+    def _selects_ok(self) -> bool:
+        """Hook, called at a host sync point: did every deferred select since the last call finish?"""
+        return True
+
+    def _stepwise_selects(self):
+        """Hook: context in which selects avoid any shortcut that _selects_ok() could reject."""
+        import contextlib
+
+        return contextlib.nullcontext()
 
     def _select(self, specs, out16, counts=None) -> None:
         """Hook: all select rows of a step in one launch sequence (ShardedSimulator adds the all-reduce)."""
@@ -592,7 +612,8 @@ class RetirementMonteCarloSimulator:
         series_bytes = 8 * n * (2 * self._trajectory_len(int(working_months)) + R0)
         free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
         sweep = self._agree(bool(bands) and (series_bytes > 0.6 * free_bytes
-                                             or os.environ.get("MCR_SERIES_SWEEP") == "1"))
+                                             or os.environ.get("MCR_SERIES_SWEEP") == "1"),
+                            key=(int(working_months), n_global, bool(bands)))
         if timeline_events is not None:
             timeline_events[0].record()
         part_first = first_path + offset
@@ -667,6 +688,8 @@ class RetirementMonteCarloSimulator:
         agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
                                wr_counts=wr_counts, rates=rates, sample_block=sample_block)
         agg.n_override = n_global
+        agg.redo = (self, dict(working_months=working_months, num_simulations=num_simulations, bands=bands,
+                               first_path=first_path, samples=samples))
         return agg
 
     def _final_balance_histograms(self, b: DeviceBatch, rng_m, rng_1, hists) -> None:
