@@ -25,11 +25,9 @@ from __future__ import annotations
 
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
-import numpy as np
 import pandas as pd
 
 from . import native
-from .constants import MONTHS_PER_YEAR
 from .simulation import (FINAL_BALANCE_QUANTILES, TRAJECTORY_QUANTILES, WITHDRAWAL_RATE_QUANTILES,
                          RetirementMonteCarloSimulator)
 
@@ -216,7 +214,7 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         packed = torch.zeros((7, m), **f64)
         packed[0:5, :n] = b.cols
         packed[5, :n] = b.success.to(torch.float64)
-        packed[6, :n] = b.ruin.to(torch.float64)
+        b.years_to_ruin_into(packed[6, :n])
         gathered = torch.empty((coll.world, 7, m), **f64)
         coll.dist.all_gather_into_tensor(gathered, packed, group=coll.group)
         host = torch.empty((7, n_global), dtype=torch.float64, pin_memory=True)
@@ -229,15 +227,12 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
             with self._stepwise_selects():
                 self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
         all_cols = host.numpy()
-        all_ruin = all_cols[6]
-        years_to_ruin = all_ruin / MONTHS_PER_YEAR
-        years_to_ruin[all_ruin < 0] = np.nan
         self.last_d2h_bytes = n_global * 7 * 8 + (2 * T * nq + R * nw + 2 * k * T + R) * 8
         summary_df = pd.DataFrame({
             "Start Balance": all_cols[0],
             "Final Balance": all_cols[1],
             "Success": all_cols[5] != 0.0,
-            "YearsToRuin": years_to_ruin,
+            "YearsToRuin": all_cols[6],
             "First Year Gross Withdrawal": all_cols[2],
             "First Year Real Gross Withdrawal": all_cols[3],
             "Inflation At Retirement": all_cols[4],

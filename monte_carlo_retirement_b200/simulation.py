@@ -168,6 +168,13 @@ class DeviceBatch:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
+    def years_to_ruin_into(self, dst) -> None:
+        """dst[i] = ruin month / 12, NaN for paths that never failed — the reference's
+        `YearsToRuin` column (simulation.py:825-828,943), filled on the device."""
+        dst.copy_(self.ruin)
+        dst.div_(float(MONTHS_PER_YEAR))
+        dst.masked_fill_(self.ruin < 0, float("nan"))
+
 
 class DeviceAggregates:
     """Device-resident aggregates of one batch (see RetirementMonteCarloSimulator.aggregates_device)."""
@@ -441,9 +448,8 @@ class RetirementMonteCarloSimulator:
         # fresh pinned blocks per call (torch's caching host allocator recycles them once the
         # previous call's DataFrame is garbage): summary_df is built on these without a copy
         return {"n": n, "stream": self._copy_stream,
-                "cols": torch.empty((5, n), dtype=torch.float64, pin_memory=True),
-                "succ": torch.empty(n, dtype=torch.uint8, pin_memory=True),
-                "ruin": torch.empty(n, dtype=torch.int32, pin_memory=True)}
+                "cols": torch.empty((6, n), dtype=torch.float64, pin_memory=True),  # 5 summary columns + YearsToRuin
+                "succ": torch.empty(n, dtype=torch.uint8, pin_memory=True)}
 
     # ---- hooks a sharded (multi-GPU) subclass overrides; identity on one GPU --------------------
     def _shard(self, n_global: int) -> Tuple[int, int]:
@@ -535,13 +541,16 @@ class RetirementMonteCarloSimulator:
         # soon as the timeline kernel is done, underneath the select kernels
         main = torch.cuda.current_stream()
         stage = self._staging(n, dev)
+        years = torch.empty(n, dtype=torch.float64, device=dev)
+        b.years_to_ruin_into(years)
         done = torch.cuda.Event()
         done.record(main)
         with torch.cuda.stream(stage["stream"]):
             stage["stream"].wait_event(done)
-            stage["cols"].copy_(b.cols, non_blocking=True)
+            stage["cols"][:5].copy_(b.cols, non_blocking=True)
+            stage["cols"][5].copy_(years, non_blocking=True)
             stage["succ"].copy_(b.success, non_blocking=True)
-            stage["ruin"].copy_(b.ruin, non_blocking=True)
+        years.record_stream(stage["stream"])
 
         # one small result block: bands (T*7 *2), WR bands (R*5), samples (k*T *2)
         small = torch.empty(2 * T * nq + R * nw + 2 * k * T, dtype=torch.float64, device=dev)
@@ -558,18 +567,14 @@ class RetirementMonteCarloSimulator:
         host_small = small.cpu()          # synchronises the main stream
         host_counts = wr_counts.cpu()
         stage["stream"].synchronize()
-        self.last_d2h_bytes = n * (5 * 8 + 1 + 4) + host_small.numel() * 8 + R * 8
+        self.last_d2h_bytes = n * (6 * 8 + 1) + host_small.numel() * 8 + R * 8
 
         c = stage["cols"].numpy()  # pinned block owned by this call's result (no copy)
-        ruin = stage["ruin"].numpy()
-        years_to_ruin = ruin.astype(np.float64)
-        years_to_ruin /= MONTHS_PER_YEAR
-        years_to_ruin[ruin < 0] = np.nan
         summary_df = pd.DataFrame({
             "Start Balance": c[0],
             "Final Balance": c[1],
-            "Success": stage["succ"].numpy().astype(bool),
-            "YearsToRuin": years_to_ruin,
+            "Success": stage["succ"].numpy().view(np.bool_),  # 0/1 bytes written by the kernel
+            "YearsToRuin": c[5],
             "First Year Gross Withdrawal": c[2],
             "First Year Real Gross Withdrawal": c[3],
             "Inflation At Retirement": c[4],
