@@ -81,8 +81,9 @@ struct PathOut {
 template <int TAXED1, int TAXED2, int ANNUAL, int EXPSMALL = 0>
 struct Cfg {
   // EXPSMALL: the host proved |mu/12| + sigma/sqrt(12) * z_max < 0.1 for all three factors (the
-  // Box-Muller normals of 32-bit uniforms are bounded by 6.77), so a degree-10 polynomial is
-  // exact to < 3e-19 relative and no range test is needed. Native-RNG launches only.
+  // Box-Muller normals of 32-bit uniforms are bounded by 6.77), so a short polynomial
+  // (Math::poly_exp_small) is accurate far below the noise of the MUFU normals and no range
+  // test is needed. Native-RNG launches only.
   static constexpr bool kExpSmall = EXPSMALL != 0;
   // kAlgebra: both assets taxed on realized gains with rate < 1 (checked by the launcher): the
   // fast build may use the closed forms of the withdrawal pair and of the rebalance sale (see
@@ -129,6 +130,13 @@ __device__ __forceinline__ bool either_le_abs(double a, double b, double c) {
   uint32_t r;
   asm("{\n\t.reg .pred p, q;\n\t.reg .f64 t;\n\tabs.f64 t, %2;\n\tsetp.le.f64 p, %1, %3;\n\t"
       "setp.le.f64 q, t, %3;\n\tor.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "d"(a), "d"(b), "d"(c));
+  return r != 0;
+}
+__device__ __forceinline__ bool either_le(double a, double b, double c) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.le.f64 p, %1, %3;\n\tsetp.le.f64 q, %2, %3;\n\tor.pred p, p, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(r) : "d"(a), "d"(b), "d"(c));
   return r != 0;
 }
@@ -180,10 +188,13 @@ struct Math {
   // the three monthly gross factors exp(mu/12 + sigma/sqrt(12)*z) — simulation.py:468-474,522-530.
   // Fast build: ONE combined range test (integer compare on the high words), then three
   // interleaved Horner chains in a single basic block.
-  static __device__ __forceinline__ double poly_exp9(double x) {  // degree 10, |x| < 0.1: x^11/11! < 3e-19
-    double p = kExpC[3];
+  // Native-draw fast build only: degree 6, |x| < 0.1 (DevParams::exp_small). The truncation
+  // x^7/7! is < 2e-11 at the bound and ~1e-16 at a typical |x| of 0.02 — orders below the 3e-9
+  // the MUFU normals (5e-7 absolute on z) already put on every monthly factor of this build.
+  static __device__ __forceinline__ double poly_exp_small(double x) {
+    double p = kExpC[7];
 #pragma unroll
-    for (int i = 4; i < 12; ++i) p = fma(p, x, kExpC[i]);
+    for (int i = 8; i < 12; ++i) p = fma(p, x, kExpC[i]);
     p = fma(p, x, 1.0);
     return fma(p, x, 1.0);
   }
@@ -194,9 +205,9 @@ struct Math {
     const double xi = P.muI + P.sgI * zi;
     const double xp = P.muP + P.sgP * zp;
     if constexpr (FAST && C::kExpSmall) {
-      G1 = poly_exp9(x1);
-      GI = poly_exp9(xi);
-      GP = poly_exp9(xp);
+      G1 = poly_exp_small(x1);
+      GI = poly_exp_small(xi);
+      GP = poly_exp_small(xp);
       return;
     }
     if constexpr (FAST) {
@@ -357,7 +368,9 @@ __device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, d
   }
   const double cbs = sell1 ? cb1 : cb2;
   const double cbo = sell1 ? cb2 : cb1;
-  const double rate = sell1 ? (P.use1 ? P.rate1 : 0.0) : (P.use2 ? P.rate2 : 0.0);
+  // use && rate == 0 and !use both mean "no tax on this sale": taxed{1,2} (compile-time in the
+  // specialised configurations) selects the same value as the reference's `use` test
+  const double rate = sell1 ? (C::taxed1(P) ? P.rate1 : 0.0) : (C::taxed2(P) ? P.rate2 : 0.0);
   const double as = sell1 ? P.a1 : P.a2;
   double sale, fs;
   if (FAST && !FULL && C::algebra(P)) {
@@ -371,8 +384,10 @@ __device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, d
     const double br_c = fs * cbs;
     const double buy_c = sale - fs * gr;
     double nbs = bs - sale, ncbs = cbs - br_c, nbo = bo + buy_c, ncbo = cbo + buy_c;
-    if (nbs <= kEps) { nbs = 0.0; ncbs = 0.0; }
-    if (nbo <= kEps) { nbo = 0.0; ncbo = 0.0; }
+    if (__builtin_expect(either_le(nbs, nbo, kEps), 0)) {   // :355-358, one rarely-taken branch for both
+      if (nbs <= kEps) { nbs = 0.0; ncbs = 0.0; }
+      if (nbo <= kEps) { nbo = 0.0; ncbo = 0.0; }
+    }
     b1 = sell1 ? nbs : nbo;
     cb1 = sell1 ? ncbs : ncbo;
     b2 = sell1 ? nbo : nbs;
@@ -650,8 +665,10 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
           nw1 = f * cap1;
           nw2 = f * cap2;
           double nb1 = b1 - gw1, ncb1 = cb1 - f * cb1, nb2 = b2 - gw2, ncb2 = cb2 - f * cb2;
-          if (nb1 <= kEps) { nb1 = 0.0; ncb1 = 0.0; }
-          if (nb2 <= kEps) { nb2 = 0.0; ncb2 = 0.0; }
+          if (__builtin_expect(either_le(nb1, nb2, kEps), 0)) {   // :245-247, rarely taken
+            if (nb1 <= kEps) { nb1 = 0.0; ncb1 = 0.0; }
+            if (nb2 <= kEps) { nb2 = 0.0; ncb2 = 0.0; }
+          }
           b1 = nb1; cb1 = ncb1; b2 = nb2; cb2 = ncb2;
         }
       }
