@@ -267,7 +267,8 @@ def run_b200_arm(args):
     def step(events=None):
         # world > 1: no data-path collective; counters, histograms and the radix-select digit
         # histograms (exact global bands) are all-reduced over NVLink inside aggregates_device
-        return sim.aggregates_device(WORKING_MONTHS, n_job, bands=True, timeline_events=events)
+        return sim.aggregates_device(WORKING_MONTHS, n_job, bands=True, timeline_events=events,
+                                     pipeline=args.pipeline)
 
     fp64_peak = ctx.fp64_peak_slots_per_s()
     for _ in range(max(args.warmup, 3)):
@@ -284,6 +285,7 @@ def run_b200_arm(args):
     t_start.record()
     for i in range(args.steps):
         agg = step(k_events[i])
+    agg.wait()  # pipelined reductions run on their own stream: the last step's must be inside the timed region
     t_end.record()
     barrier()
     clocks = sampler.stop()
@@ -389,6 +391,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=0, choices=[0, 1],
+                    help="1: reductions of step i on a second stream, under the timeline kernel of step i+1")
     args = ap.parse_args()
     _silence_logs()
     if args.impl == "reference":

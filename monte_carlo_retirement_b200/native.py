@@ -161,7 +161,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     with _lib_lock:
         if _lib is not None and path is None:
             return _lib
-        p = path or LIB_PATH
+        p = path or os.environ.get("MCR_LIB") or LIB_PATH  # MCR_LIB: an alternative build (tuning experiments)
         if not os.path.exists(p):
             raise RuntimeError(
                 f"{p} is missing: build it with `python -m monte_carlo_retirement_b200.build` "

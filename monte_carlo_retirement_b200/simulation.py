@@ -182,8 +182,17 @@ class DeviceAggregates:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
+    def wait(self) -> None:
+        """Make the current stream wait for a pipelined call's reductions."""
+        if getattr(self, "ready", None) is not None:
+            import torch
+
+            torch.cuda.current_stream().wait_event(self.ready)
+
     def to_host(self) -> Dict[str, Any]:
         sim, args = getattr(self, "redo", (None, None))
+        if getattr(self, "ready", None) is not None:
+            self.ready.synchronize()  # pipelined call: the reductions ran on their own stream
         if sim is not None:
             import torch
 
@@ -601,13 +610,20 @@ class RetirementMonteCarloSimulator:
 
     # ---- aggregate-only mode: nothing N-sized leaves the device ----------
     def aggregates_device(self, working_months: int, num_simulations: int, *, bands: bool = True,
-                          first_path: int = 0, timeline_events=None, samples: bool = False) -> "DeviceAggregates":
+                          first_path: int = 0, timeline_events=None, samples: bool = False,
+                          pipeline: bool = False) -> "DeviceAggregates":
         """Enqueue one batch and every device-side reduction the callers make over summary_df
         (server.py:439-461,525-532; main.py:112-133; utils.py:97-102; plotting.py:46-59;
         HistogramChart.jsx:13-60). Nothing is copied to the host and nothing synchronises.
         `timeline_events=(start, end)` records CUDA events around the timeline kernel;
         `samples=True` (with bands) also keeps the 5 sampled nominal / real paths of
-        simulation.py:1063-1078 — 2 x 5 x T values, the only per-path data the payload needs."""
+        simulation.py:1063-1078 — 2 x 5 x T values, the only per-path data the payload needs.
+        `pipeline=True` enqueues the reductions on a second (high-priority) stream, so that a
+        caller looping over batches gets the HBM-bound reductions of batch i underneath the
+        issue-bound timeline kernel of batch i+1; the result then carries a `ready` event that
+        `to_host()` / `wait()` honour."""
+        import contextlib
+
         import torch
 
         ctx = self.native_context
@@ -625,6 +641,38 @@ class RetirementMonteCarloSimulator:
         b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=part_first)
         if timeline_events is not None:
             timeline_events[1].record()
+        side = None
+        if pipeline:
+            side = self._reduction_stream()
+            produced = torch.cuda.Event()
+            produced.record()
+            side.wait_event(produced)
+            for t in (b.cols, b.success, b.ruin, b.counters, b.traj, b.real, b.wr):
+                if t is not None:
+                    t.record_stream(side)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            agg = self._aggregate_batch(b, n_global, offset, working_months, bands, sweep, samples, part_first)
+            if side is not None:
+                agg.ready = torch.cuda.Event()
+                agg.ready.record(side)
+        agg.redo = (self, dict(working_months=working_months, num_simulations=num_simulations, bands=bands,
+                               first_path=first_path, samples=samples))
+        return agg
+
+    def _reduction_stream(self):
+        import torch
+
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self._torch_device(), priority=-1)
+        return self._side_stream
+
+    def _aggregate_batch(self, b: DeviceBatch, n_global: int, offset: int, working_months: int, bands: bool,
+                         sweep: bool, samples: bool, part_first: int) -> "DeviceAggregates":
+        """Every reduction of aggregates_device over one resident batch, on the current stream."""
+        import torch
+
+        ctx = self.native_context
+        n = b.n
         self._reduce_counts(b.counters)
         dev = b.cols.device
         T, R = b.T, b.R
@@ -693,8 +741,6 @@ class RetirementMonteCarloSimulator:
         agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
                                wr_counts=wr_counts, rates=rates, sample_block=sample_block)
         agg.n_override = n_global
-        agg.redo = (self, dict(working_months=working_months, num_simulations=num_simulations, bands=bands,
-                               first_path=first_path, samples=samples))
         return agg
 
     def _final_balance_histograms(self, b: DeviceBatch, rng_m, rng_1, hists) -> None:
