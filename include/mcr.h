@@ -254,7 +254,8 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
                        double* out_dev, int64_t* counts_dev, void* stream);
 
 /* The same select one step at a time, for path shards spread over several GPUs:
- *   BEGIN; for pass in 0..7 { if pass == mcr_select_full_passes(): COLLECT ;
+ *   BEGIN; for pass in 0..7 (0..9 with the EXTREMES exchange below) {
+ *   if pass == mcr_select_full_passes(): COLLECT ;
  *   HIST (local shard) ; all-reduce(sum) hist_dev across ranks ; ADVANCE } ; FINISH.
  * After the all-reduce every rank holds the GLOBAL digit histogram, so all ranks walk to the
  * same exact global order statistics without moving any path data (COLLECT gathers the local
@@ -272,8 +273,9 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
 /* Optional (BEGIN with pass = 1): after HIST of pass 0, EXTREMES_GET writes every row's local
  * (min, max) key into out_dev as int64[n_rows][2] in an encoding whose element-wise MIN over
  * ranks is the global pair; all-reduce(MIN) it and hand it back with EXTREMES_SET before
- * ADVANCE 0. The select then skips the key bits all elements share (constant rows finish at
- * once, concentrated rows need no extra scans). */
+ * ADVANCE 0. Pass 0 then only looks at (a sample of) every row for its extreme keys and the
+ * select skips the key bits they share — concentrated rows need no extra scans; keys outside
+ * that prefix are accounted for exactly by the next pass, which also counts the row. */
 #define MCR_SELECT_EXTREMES_GET 5
 #define MCR_SELECT_EXTREMES_SET 6
 /* Pooled tail (BEGIN with pass = 3: adaptive start + pooled tail). Rows stop scanning as soon as

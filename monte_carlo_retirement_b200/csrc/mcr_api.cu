@@ -553,7 +553,7 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
   std::lock_guard<std::mutex> lk(ctx->mu);
   const bool pooled_step = step >= MCR_SELECT_POOL_EXPORT && step <= MCR_SELECT_POOL_TAIL;
   const int rank = pass & 0xff, world = (pass >> 8) & 0xff;  // POOL_* steps: pass = rank | world << 8
-  if (pooled_step ? (world < 1 || rank >= world) : (pass < 0 || pass > 7)) return fail(ctx, MCR_EINVAL, "bad pass");
+  if (pooled_step ? (world < 1 || rank >= world) : (pass < 0 || pass > 15)) return fail(ctx, MCR_EINVAL, "bad pass");
   std::vector<RowDesc> d;
   if (int rc = make_descs(ctx, rows_host, n_rows, d)) return rc;
   int64_t max_n = 0;

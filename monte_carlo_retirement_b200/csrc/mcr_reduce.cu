@@ -88,6 +88,10 @@ constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
 constexpr int kBigBucket = 2048;    // buckets above this are not gathered (resolved by min == max, else by scanning)
 constexpr int kFullPasses = 4;      // passes that may scan the rows before the collect (pass 0 + up to 3 digits)
 constexpr int kHistWords = kMaxTargets * 256;  // per row
+constexpr int kSampleStride = 16;   // adaptive pass 0 reads every 16th chunk of a long row ...
+constexpr int kSampleMinChunks = 8; // ... rows of up to 8 chunks are read whole
+constexpr int kMaxCommonBits = 56;  // the first digit pass always has a digit left to count with
+constexpr int kBelowAt = 256, kAboveAt = 257;  // H slots of the keys outside the sampled prefix (first digit pass)
 
 __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, const RowDesc* __restrict__ desc,
                            int adaptive, int fused) {
@@ -263,16 +267,16 @@ __device__ __forceinline__ void hist_dispatch(const Probe& P, const double* __re
   }
 }
 
-// adaptive pass 0: no digit yet — count the valid elements and take the row's extreme keys
+// adaptive pass 0: no digit yet — the extreme keys of (a sample of) the row. The leading bits the
+// two share are very likely shared by every key of the row; the first digit pass verifies that
+// exactly (keys outside are counted as below / above) and counts the valid elements.
 template <int NT, bool MASKED>
 __device__ __forceinline__ void extremes_elements(const double* __restrict__ x, const uint8_t* __restrict__ m, int cnt,
-                                                  SelRow& R, uint32_t* H) {
+                                                  SelRow& R) {
   uint64_t lo_k = ~0ull, hi_k = 0ull;
-  uint32_t n_ok = 0;
   scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
     const uint64_t k = ((uint64_t)hi << 32) | lo;
     if (ok) {
-      ++n_ok;
       lo_k = k < lo_k ? k : lo_k;
       hi_k = k > hi_k ? k : hi_k;
     }
@@ -282,13 +286,38 @@ __device__ __forceinline__ void extremes_elements(const double* __restrict__ x, 
     const uint64_t l2 = __shfl_xor_sync(0xffffffffu, lo_k, o), h2 = __shfl_xor_sync(0xffffffffu, hi_k, o);
     lo_k = l2 < lo_k ? l2 : lo_k;
     hi_k = h2 > hi_k ? h2 : hi_k;
-    n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
   }
-  if ((threadIdx.x & 31) == 0 && n_ok) {
-    atomicAdd(&H[0], n_ok);  // bin 0 of group 0 carries the count (summed like any histogram)
+  if ((threadIdx.x & 31) == 0 && lo_k <= hi_k) {
     atomicMin((unsigned long long*)&R.kmin, (unsigned long long)lo_k);
     atomicMax((unsigned long long*)&R.kmax, (unsigned long long)hi_k);
   }
+}
+
+// first digit pass of an adaptive row: digit histogram of the keys that carry the sampled
+// prefix, and the number of keys below / above it
+template <int NT, bool MASKED>
+__device__ __forceinline__ void first_digit_elements(const Probe& P, const double* __restrict__ x,
+                                                     const uint8_t* __restrict__ m, int cnt) {
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
+    int id = -1;
+    if (ok) {
+      const uint32_t d_hi = (hi ^ P.p_hi) & P.m_hi, d_lo = (lo ^ P.p_lo) & P.m_lo;
+      const uint64_t k = ((uint64_t)hi << 32) | lo;
+      if ((d_hi | d_lo) == 0u) {
+        id = (int)((uint32_t)(k >> P.dshift) & P.dmask);
+      } else {  // first differing bit decides the side: the key has a 1 where the prefix has a 0 <=> above
+        const uint64_t kp = k & (((uint64_t)P.m_hi << 32) | P.m_lo), pp = ((uint64_t)P.p_hi << 32) | P.p_lo;
+        id = kp > pp ? kAboveAt : kBelowAt;
+      }
+    }
+    const int id0 = __shfl_sync(0xffffffffu, id, 0);
+    if (__all_sync(0xffffffffu, id == id0)) {
+      if (id0 >= 0 && lane0) red_shared_add(P.a_hist + (uint32_t)id0 * 4u, 32u);
+    } else if (id >= 0) {
+      red_shared_add(P.a_hist + (uint32_t)id * 4u, 1u);
+    }
+  });
 }
 
 // One pass, first half: histogram of the next digit inside every live prefix bucket. Rows that
@@ -311,17 +340,27 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
   const double* __restrict__ x = (from_cand ? cand + (size_t)blockIdx.y * kCandCap : R.d.x) + begin;
   const uint8_t* __restrict__ m = (from_cand || !R.d.mask) ? nullptr : R.d.mask + begin;
   if (pass == 0 && R.adaptive) {
-    if (m) extremes_elements<kHistThreads, true>(x, m, cnt, R, H); else extremes_elements<kHistThreads, false>(x, m, cnt, R, H);
+    // a long row is sampled: every kSampleStride-th chunk (what the sample misses is handled
+    // exactly by the below / above counts of the next pass)
+    const int64_t chunks = (n + kChunk - 1) / kChunk;
+    if (chunks > kSampleMinChunks && (blockIdx.x % kSampleStride) != 0) return;
+    if (m) extremes_elements<kHistThreads, true>(x, m, cnt, R); else extremes_elements<kHistThreads, false>(x, m, cnt, R);
     return;
   }
+  const bool first_digit = pass == 1 && R.adaptive && rb > 0;  // counts keys outside the sampled prefix too
   const int ng = R.n_groups;
-  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads) sh[k] = 0;
+  const int used = first_digit ? 2 * 256 : ng * 256;
+  for (int k = threadIdx.x; k < used; k += kHistThreads) sh[k] = 0;
   if (rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
   const int w = 64 - rb < 8 ? 64 - rb : 8;
   const Probe P = make_probe(R, rb, w, T, sh);
-  hist_dispatch<kHistThreads>(P, x, m, cnt, rb, ng);
+  if (first_digit) {
+    if (m) first_digit_elements<kHistThreads, true>(P, x, m, cnt); else first_digit_elements<kHistThreads, false>(P, x, m, cnt);
+  } else {
+    hist_dispatch<kHistThreads>(P, x, m, cnt, rb, ng);
+  }
   __syncthreads();
-  for (int k = threadIdx.x; k < ng * 256; k += kHistThreads)
+  for (int k = threadIdx.x; k < used; k += kHistThreads)
     if (sh[k]) atomicAdd(&H[k], sh[k]);
 }
 
@@ -419,69 +458,98 @@ __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   }
 }
 
+// the 0-based order statistics a row asks for, given its valid count: (lo, hi) per quantile,
+// then rank-sorted so that prefixes stay sorted in every pass (for small n the pairs of
+// different quantiles interleave). One thread.
+__device__ void set_target_ranks(SelRow& R, int64_t nv) {
+  const QuantileSpec& spec = R.d.spec;
+  const int nq = spec.n_q, nt = 2 * nq;
+  R.n_valid = nv;
+  for (int q = 0; q < nq; ++q) {
+    int64_t lo = 0, hi = 0;
+    if (nv > 0) {
+      if (spec.median) {  // np.median: mean of the two middle order statistics
+        lo = (nv - 1) / 2;
+        hi = nv / 2;
+      } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
+        const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
+        if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
+        else if (vi < 0) { lo = hi = 0; }
+        else { lo = (int64_t)floor(vi); hi = lo + 1; }
+      }
+    }
+    R.rank[2 * q] = lo;
+    R.rank[2 * q + 1] = hi;
+  }
+  int32_t ord[kMaxTargets];
+  for (int t = 0; t < nt; ++t) ord[t] = t;
+  for (int i = 1; i < nt; ++i) {  // tiny insertion sort
+    const int32_t o = ord[i];
+    const int64_t r = R.rank[o];
+    int j = i - 1;
+    while (j >= 0 && R.rank[ord[j]] > r) { ord[j + 1] = ord[j]; --j; }
+    ord[j + 1] = o;
+  }
+  int64_t sorted[kMaxTargets];
+  for (int t = 0; t < nt; ++t) sorted[t] = R.rank[ord[t]];
+  for (int t = 0; t < nt; ++t) {
+    R.rank[t] = sorted[t];
+    R.slot[ord[t]] = t;
+  }
+}
+
 // One pass, second half (one warp per target + housekeeping): consume the merged histogram H
 // of row R. Needs >= 32 * (2 * n_q) threads; ends with H cleared and the next pass's groups set.
+//   adaptive rows:  pass 0 took (sampled) extreme keys -> the common prefix, nothing counted yet;
+//                   pass 1 histogrammed the first digit below that prefix, plus the keys outside
+//                   it -> valid count, target ranks, first walk. A target that falls outside the
+//                   sampled prefix (only possible if the sample missed that much of the row)
+//                   restarts the row from bit 0 as a non-adaptive one;
+//   other rows:     pass 0 histogrammed the top digit -> valid count, target ranks, first walk.
 __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
+  __shared__ int s_restart;
   const QuantileSpec& spec = R.d.spec;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int nq = spec.n_q, nt = 2 * nq;
+  const int nt = 2 * spec.n_q;
   const int rb = R.rb;
-  // adaptive pass 0 only counted the valid elements (H[0]) and took the row's extreme keys
-  const bool counted_only = pass == 0 && R.adaptive;
+  const bool adaptive = R.adaptive != 0;
+  const bool extremes_only = adaptive && pass == 0;
+  const bool first_digit = adaptive && pass == 1 && rb > 0;       // below / above slots are live
+  const bool counts_now = adaptive ? pass == 1 : pass == 0;       // this histogram carries the valid count
+  if (tid == 0) s_restart = 0;
+  __syncthreads();
   if (rb < 64 && !R.ready) {
-    if (pass == 0) {
+    if (counts_now) {
       if (warp == 0) {
         int64_t part = 0;
         for (int d = lane; d < 256; d += 32) part += H[d];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
-          const int64_t nv = part;
-          R.n_valid = nv;
-          for (int q = 0; q < nq; ++q) {
-            int64_t lo = 0, hi = 0;
-            if (nv > 0) {
-              if (spec.median) {  // np.median: mean of the two middle order statistics
-                lo = (nv - 1) / 2;
-                hi = nv / 2;
-              } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
-                const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
-                if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
-                else if (vi < 0) { lo = hi = 0; }
-                else { lo = (int64_t)floor(vi); hi = lo + 1; }
-              }
+          const int64_t below = first_digit ? (int64_t)H[kBelowAt] : 0, above = first_digit ? (int64_t)H[kAboveAt] : 0;
+          set_target_ranks(R, part + below + above);
+          if (!adaptive) {
+            for (int t = 0; t < nt; ++t) { R.prefix[t] = 0; R.group[t] = 0; }
+          } else {
+            // ranks inside the prefix bucket; a target outside it restarts the row
+            for (int t = 0; t < nt; ++t) {
+              if (R.n_valid > 0 && (R.rank[t] < below || R.rank[t] >= below + part)) s_restart = 1;
+              R.rank[t] -= below;
             }
-            R.rank[2 * q] = lo;
-            R.rank[2 * q + 1] = hi;
-          }
-          // rank-sort the targets (tiny insertion sort) so that prefixes stay sorted in every
-          // pass; for small n the (lo, hi) pairs of different quantiles interleave.
-          int32_t ord[kMaxTargets];
-          for (int t = 0; t < nt; ++t) ord[t] = t;
-          for (int i = 1; i < nt; ++i) {
-            const int32_t o = ord[i];
-            const int64_t r = R.rank[o];
-            int j = i - 1;
-            while (j >= 0 && R.rank[ord[j]] > r) { ord[j + 1] = ord[j]; --j; }
-            ord[j + 1] = o;
-          }
-          int64_t sorted[kMaxTargets];
-          for (int t = 0; t < nt; ++t) sorted[t] = R.rank[ord[t]];
-          for (int t = 0; t < nt; ++t) {
-            R.rank[t] = sorted[t];
-            R.slot[ord[t]] = t;
-            R.prefix[t] = 0;
-            R.group[t] = 0;
+            if (s_restart) {
+              for (int t = 0; t < nt; ++t) { R.rank[t] += below; R.prefix[t] = 0; R.group[t] = 0; R.bcount[t] = R.n_valid; }
+            }
           }
         }
       }
       __syncthreads();
     }
+    const bool restart = s_restart != 0;
     // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
     // holding its rank
     const int w = 64 - rb < 8 ? 64 - rb : 8;
-    if (!counted_only && warp < nt && R.n_valid > 0) {
+    if (!extremes_only && !restart && warp < nt && R.n_valid > 0) {
       const uint32_t* h = H + R.group[warp] * 256;
       uint32_t c[8];
       uint32_t local = 0;
@@ -514,18 +582,25 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
     __syncthreads();
     if (tid == 0) {
       int nrb = rb + w;
-      if (R.n_valid <= 0) {
-        nrb = 64;
-      } else if (counted_only) {
-        // every key shares the leading clz(kmin ^ kmax) bits: they are resolved for free, and all
-        // elements are in every target's bucket (ranks unchanged). A constant row is done.
+      bool counted = true;
+      if (extremes_only) {
+        // the keys seen share the leading clz(kmin ^ kmax) bits: resolved for free (at most
+        // kMaxCommonBits, so that the next pass still has a digit to count the row with).
+        // Nothing seen (empty / all-NaN sample): start from bit 0.
         const uint64_t x = R.kmin ^ R.kmax;
-        const int c = x ? __clzll((long long)x) : 64;
+        int c = R.kmin > R.kmax ? 0 : (x ? __clzll((long long)x) : 64);
+        c = c > kMaxCommonBits ? kMaxCommonBits : c;
         nrb = c;
         for (int t = 0; t < nt; ++t) {
-          R.prefix[t] = c == 0 ? 0ull : (c == 64 ? R.kmin : (R.kmin >> (64 - c)));
-          R.bcount[t] = R.n_valid;
+          R.prefix[t] = c == 0 ? 0ull : (R.kmin >> (64 - c));
+          R.bcount[t] = 0;
         }
+        counted = false;
+      } else if (restart) {
+        nrb = 0;
+        R.adaptive = 0;
+      } else if (R.n_valid <= 0) {
+        nrb = 64;
       }
       R.rb = nrb;
       // groups of the next pass (targets are rank-sorted, so prefixes are sorted)
@@ -546,8 +621,8 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
       // repeated value — zero-padded failed paths — never shrinks)
       // (only where a tail kernel finishes the row from the gathered list: the plain stepwise
       // protocol keeps histogramming, so it has no use for an early stop)
-      const bool ready = R.fused && nrb < 64 && total <= kCandCap;
-      for (int k = 0; k < g; ++k) R.gbig[k] = (!ready && gcount[k] > kBigBucket) ? 1 : 0;
+      const bool ready = counted && !restart && R.fused && nrb < 64 && total <= kCandCap;
+      for (int k = 0; k < g; ++k) R.gbig[k] = (!ready && (!counted || restart || gcount[k] > kBigBucket)) ? 1 : 0;
       R.ready = ready ? 1 : 0;
     }
   }

@@ -388,7 +388,9 @@ class Context:
             if int(xbuf[0].item()) == 0:  # identical on every rank: all of them saw the same pool
                 return None
         step(0, 1 if adaptive else 0)
-        for p in range(8):
+        # 8 digits of 8 bits resolve any key; the adaptive start spends pass 0 on the row extremes
+        # and may give up its prefix after pass 1 (mcr_reduce.cu: advance_row), hence 2 more
+        for p in range(10 if adaptive else 8):
             if p == full:
                 step(4)  # COLLECT: candidates of the resolved prefixes (local shard)
             step(1, p)

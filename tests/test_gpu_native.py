@@ -237,6 +237,49 @@ def test_quantiles_match_pandas_bit_for_bit(n):
     assert (np.isnan(want_med) and np.isnan(med.item())) or med.item() == want_med
 
 
+def test_quantiles_of_long_rows_are_exact_whatever_the_sampled_extremes_miss():
+    """Rows longer than 8 chunks take their adaptive start from a SAMPLE (every 16th chunk of
+    16384 elements); the first digit pass accounts for everything outside the sampled prefix
+    exactly and a target that falls outside it restarts the row. Adversarial layouts, bit for
+    bit against pandas."""
+    import torch
+
+    n, chunk = 400_000, 16384
+    rng = np.random.default_rng(99)
+    sampled = np.zeros(n, dtype=bool)
+    for c0 in range(0, n, 16 * chunk):
+        sampled[c0:c0 + chunk] = True
+    base = np.exp(rng.normal(13, 0.4, n))
+    rows = []
+    rows.append(base.copy())                                   # 0: ordinary i.i.d. row
+    rows.append(np.sort(base))                                 # 1: ascending
+    rows.append(np.sort(base)[::-1].copy())                    # 2: descending
+    r = base.copy(); r[~sampled] = np.where(rng.random((~sampled).sum()) < 0.45, 1e-3 * base[~sampled], base[~sampled])
+    rows.append(r)                                             # 3: 40 % of the mass far BELOW anything the sample sees
+    r = base.copy(); r[~sampled][:0] = 0; idx = np.flatnonzero(~sampled)[:10]; r[idx] = 0.0
+    rows.append(r)                                             # 4: ten zeros the sample misses (stay 'below', no restart)
+    r = base.copy(); r[sampled] = np.nan
+    rows.append(r)                                             # 5: the sample sees no valid element at all
+    r = base.copy(); r[sampled] = 5.0e5
+    rows.append(r)                                             # 6: the sample sees ONE value, the row varies
+    r = base.copy(); r[~sampled] = -base[~sampled]
+    rows.append(r)                                             # 7: everything negative outside the sample
+    x = np.stack(rows)
+    q = [0.0, 0.05, 0.10, 0.25, 0.50, 0.75, 0.90, 0.95, 1.0]
+    sim = make_sim(scenarios.TEST_BASE)
+    out = torch.empty((len(rows), len(q)), dtype=torch.float64, device="cuda")
+    cnt = torch.empty(len(rows), dtype=torch.int64, device="cuda")
+    sim.native_context.quantiles(_dev(x), n, n, len(rows), q, out, counts=cnt)
+    want = pd.DataFrame(x.T).quantile(q, axis=0).T.to_numpy()
+    got = out.cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True), np.argwhere(got != want)
+    assert cnt.cpu().tolist() == pd.DataFrame(x.T).count().tolist()
+    med = torch.empty(1, dtype=torch.float64, device="cuda")
+    mask = np.ones(n, dtype=np.uint8); mask[sampled] = 0
+    sim.native_context.quantiles(_dev(x[0]), n, n, 1, [0.5], med, median=True, mask=_dev(mask))   # masked-out sample
+    assert med.item() == np.median(x[0][~sampled])
+
+
 def test_histograms_match_numpy_and_frontend_rule():
     import torch
 
