@@ -97,7 +97,7 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
                  **kw):
         super().__init__(params_model, main_seed_override, **kw)
         self.coll = collectives or Collectives()
-        self._agreed: Dict[Any, bool] = {}
+        self._agreed: Dict[Any, int] = {}
         self._select_flag = None
         self._stepwise_only = False
         self._sign4 = None
@@ -118,13 +118,13 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def _shard(self, n_global: int) -> Tuple[int, int]:
         return shard_range(int(n_global), self.coll.rank, self.coll.world)
 
-    def _agree(self, flag: bool, key=None) -> bool:
+    def _agree_min(self, value: int, key=None) -> int:
         import torch
 
         if key is not None and key in self._agreed:
             return self._agreed[key]
-        t = torch.tensor([int(bool(flag))], dtype=torch.int32, device=self._torch_device())
-        out = bool(self.coll.max_(t).item())
+        t = torch.tensor([int(value)], dtype=torch.int64, device=self._torch_device())
+        out = int(self.coll.min_(t).item())
         if key is not None:
             self._agreed[key] = out
         return out

@@ -415,9 +415,14 @@ class RetirementMonteCarloSimulator:
         success = torch.empty(n, dtype=torch.uint8, device=dev)
         ruin = torch.empty(n, dtype=torch.int32, device=dev)
         counters = torch.zeros(2 + 12 * R + 1, dtype=torch.int64, device=dev)  # success, executed, ruin hist
-        # series: True (all three), False (none) or one of "traj" / "real" / "wr" (huge batches
-        # whose three series do not fit in HBM together are swept one series at a time)
-        want = {"traj", "real", "wr"} if series is True else (set() if not series else {series})
+        # series: True (all three), False (none), one of "traj" / "real" / "wr" or a tuple of them
+        # (huge batches whose three series do not fit in HBM together are swept in several passes)
+        if series is True:
+            want = {"traj", "real", "wr"}
+        elif not series:
+            want = set()
+        else:
+            want = {series} if isinstance(series, str) else set(series)
         traj = torch.empty((T, n), **f64) if "traj" in want else None
         real = torch.empty((T, n), **f64) if "real" in want else None
         wr = torch.empty((R, n), **f64) if "wr" in want else None
@@ -465,9 +470,40 @@ class RetirementMonteCarloSimulator:
         """(offset, count) of the global path range this process owns."""
         return 0, n_global
 
-    def _agree(self, flag: bool, key=None) -> bool:
-        """A decision every rank must take the same way (`key`: remember it for this call shape)."""
-        return bool(flag)
+    def _agree_min(self, value: int, key=None) -> int:
+        """A quantity every rank must plan with identically: the minimum over ranks (`key`:
+        remember it for this call shape)."""
+        return int(value)
+
+    def _series_plan(self, n: int, T: int, R: int, bands: bool, key) -> List[Tuple[str, ...]]:
+        """Which of the three yearly series each timeline pass materialises. One pass when they
+        fit in HBM together (1.3 KB per path at C3); otherwise they are packed, in order, into as
+        few recomputed passes as 70 % of the free memory (minimum over ranks) allows — e.g. 1.25e8
+        paths x 71 points: [traj] then [real, wr]. Philox makes every (path, month) draw
+        reproducible, so a recomputed pass costs kernel time, not memory or precision."""
+        import torch
+
+        if not bands:
+            return [()]
+        sizes = {"traj": 8 * n * T, "real": 8 * n * T, "wr": 8 * n * R}
+        free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
+        budget = int(0.7 * free_bytes)
+        if os.environ.get("MCR_SERIES_BUDGET_BYTES"):
+            budget = int(os.environ["MCR_SERIES_BUDGET_BYTES"])
+        if os.environ.get("MCR_SERIES_SWEEP") == "1":
+            budget = 0  # one series per pass
+        budget = self._agree_min(budget, key)
+        plan: List[Tuple[str, ...]] = []
+        cur: List[str] = []
+        used = 0
+        for name in ("traj", "real", "wr"):
+            if cur and used + sizes[name] > budget:
+                plan.append(tuple(cur))
+                cur, used = [], 0
+            cur.append(name)
+            used += sizes[name]
+        plan.append(tuple(cur))
+        return plan
 
     def _selects_ok(self) -> bool:
         """Hook, called at a host sync point: did every deferred select since the last call finish?"""
@@ -629,16 +665,14 @@ class RetirementMonteCarloSimulator:
         ctx = self.native_context
         n_global = int(num_simulations)
         offset, n = self._shard(n_global)  # single GPU: (0, n_global)
-        R0 = self.params_model.retirement_years
-        series_bytes = 8 * n * (2 * self._trajectory_len(int(working_months)) + R0)
-        free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
-        sweep = self._agree(bool(bands) and (series_bytes > 0.6 * free_bytes
-                                             or os.environ.get("MCR_SERIES_SWEEP") == "1"),
-                            key=(int(working_months), n_global, bool(bands)))
+        plan = self._series_plan(n, self._trajectory_len(int(working_months)), self.params_model.retirement_years,
+                                 bool(bands), key=(int(working_months), n_global, bool(bands)))
+        self.last_series_plan = plan
         if timeline_events is not None:
             timeline_events[0].record()
         part_first = first_path + offset
-        b = self.run_batch_device(working_months, n, series=(bands and not sweep), first_path=part_first)
+        b = self.run_batch_device(working_months, n, series=(True if len(plan[0]) == 3 else (plan[0] or False)),
+                                  first_path=part_first)
         if timeline_events is not None:
             timeline_events[1].record()
         side = None
@@ -651,7 +685,7 @@ class RetirementMonteCarloSimulator:
                 if t is not None:
                     t.record_stream(side)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            agg = self._aggregate_batch(b, n_global, offset, working_months, bands, sweep, samples, part_first)
+            agg = self._aggregate_batch(b, n_global, offset, working_months, bands, plan, samples, part_first)
             if side is not None:
                 agg.ready = torch.cuda.Event()
                 agg.ready.record(side)
@@ -667,7 +701,7 @@ class RetirementMonteCarloSimulator:
         return self._side_stream
 
     def _aggregate_batch(self, b: DeviceBatch, n_global: int, offset: int, working_months: int, bands: bool,
-                         sweep: bool, samples: bool, part_first: int) -> "DeviceAggregates":
+                         plan: List[Tuple[str, ...]], samples: bool, part_first: int) -> "DeviceAggregates":
         """Every reduction of aggregates_device over one resident batch, on the current stream."""
         import torch
 
@@ -687,7 +721,7 @@ class RetirementMonteCarloSimulator:
         # cohorts), the 9 final-balance quantiles and, when the series are resident, the bands
         specs = [(rates, n, None, [0.5], True), (b.cols[0], n, None, [0.5], True),
                  (b.cols[1], n, b.success, [0.5], True), (b.cols[1], n, None, FINAL_BALANCE_QUANTILES, False)]
-        with_bands = bool(bands) and not sweep
+        with_bands = bool(bands) and len(plan) == 1
         if with_bands:
             specs += (ctx.series_rows(b.traj, n, T, TRAJECTORY_QUANTILES) + ctx.series_rows(b.real, n, T, TRAJECTORY_QUANTILES)
                       + ctx.series_rows(b.wr, n, R, WITHDRAWAL_RATE_QUANTILES))
@@ -717,24 +751,35 @@ class RetirementMonteCarloSimulator:
                 band_block[2 * T * nq:].view(R, nw).copy_(out16[4 + 2 * T:, :nw])
                 wr_counts.copy_(cnt_all[4 + 2 * T:])
             else:
-                # the three series do not fit together (e.g. 1.25e8 paths x 71 points = 71 GB each):
-                # recompute the batch once per series — Philox makes every (path, month) draw
-                # reproducible, so this costs kernel time, not memory or precision
-                for which, rows, qs, off in (("traj", T, TRAJECTORY_QUANTILES, 0),
-                                             ("real", T, TRAJECTORY_QUANTILES, T * nq),
-                                             ("wr", R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)):
-                    part = self.run_batch_device(working_months, n, series=which, first_path=part_first)
-                    o16 = torch.empty((rows, 16), **f64)
-                    c16 = torch.empty(rows, dtype=torch.int64, device=dev)
-                    self._select(ctx.series_rows(getattr(part, which), n, rows, qs), o16, c16)
-                    band_block[off:off + rows * len(qs)].view(rows, len(qs)).copy_(o16[:, :len(qs)])
-                    if which == "wr":
-                        wr_counts.copy_(c16)
-                    elif sample_block is not None:
-                        self._gather_samples(getattr(part, which), n, T, offset, n_global,
-                                             sample_block[0 if which == "traj" else 1])
-                    torch.cuda.current_stream().synchronize()  # release the series before the next one
-                    del part
+                # the three series do not fit together: one multi-row select per pass of the plan;
+                # the first pass's series came with the summary batch, the others are recomputed
+                layout = {"traj": (T, TRAJECTORY_QUANTILES, 0), "real": (T, TRAJECTORY_QUANTILES, T * nq),
+                          "wr": (R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)}
+                for k, group in enumerate(plan):
+                    part = b if k == 0 else self.run_batch_device(working_months, n, series=group,
+                                                                  first_path=part_first)
+                    specs_g, n_rows = [], 0
+                    for which in group:
+                        rows, qs, _ = layout[which]
+                        specs_g += ctx.series_rows(getattr(part, which), n, rows, qs)
+                        n_rows += rows
+                    o16 = torch.empty((n_rows, 16), **f64)
+                    c16 = torch.empty(n_rows, dtype=torch.int64, device=dev)
+                    self._select(ctx.select_rows(specs_g), o16, c16)
+                    at = 0
+                    for which in group:
+                        rows, qs, off = layout[which]
+                        band_block[off:off + rows * len(qs)].view(rows, len(qs)).copy_(o16[at:at + rows, :len(qs)])
+                        if which == "wr":
+                            wr_counts.copy_(c16[at:at + rows])
+                        elif sample_block is not None:
+                            self._gather_samples(getattr(part, which), n, T, offset, n_global,
+                                                 sample_block[0 if which == "traj" else 1])
+                        at += rows
+                    torch.cuda.current_stream().synchronize()  # release these series before the next pass
+                    for which in group:
+                        setattr(part, which, None)
+                    del part, specs_g
         self._last_batch = b
         if sample_block is not None:
             self._reduce_samples(sample_block)

@@ -437,6 +437,18 @@ def test_series_sweep_mode_equals_all_at_once(monkeypatch):
         assert np.array_equal(a[k].to_numpy(), b[k].to_numpy(), equal_nan=True), k
     assert a["withdrawal_rate_counts"] == b["withdrawal_rate_counts"]
     assert a["success_count"] == b["success_count"]
+    # a budget that holds two series: [traj, real] with the summary pass, [wr] recomputed
+    monkeypatch.delenv("MCR_SERIES_SWEEP")
+    T = len(a["trajectory_bands"])
+    monkeypatch.setenv("MCR_SERIES_BUDGET_BYTES", str(8 * 30_000 * 2 * T + 1))
+    assert sim._series_plan(30_000, T, 40, True, None) == [("traj", "real"), ("wr",)]
+    c = sim.run_aggregates(100, 30_000, samples=True)
+    for k in ("trajectory_bands", "real_trajectory_bands", "withdrawal_rate_bands"):
+        assert np.array_equal(a[k].to_numpy(), c[k].to_numpy(), equal_nan=True), k
+    assert a["withdrawal_rate_counts"] == c["withdrawal_rate_counts"]
+    monkeypatch.delenv("MCR_SERIES_BUDGET_BYTES")
+    d = sim.run_aggregates(100, 30_000, samples=True)
+    assert c["sample_paths"] == d["sample_paths"] and c["real_sample_paths"] == d["real_sample_paths"]
 
 
 def test_large_batch_aggregate_only_mode():

@@ -64,7 +64,8 @@ def main():
             summary["median_trajectory_last"] = float(out["trajectory_bands"][0.5].iloc[-1])
         print(json.dumps({"paths": a.paths, "n_gpus": world, "working_months": a.wm, "wall_s": dt,
                           "nominal_path_months_per_s": a.paths * months / dt,
-                          "executed_path_months": out["executed_path_months"], "result": summary}))
+                          "executed_path_months": out["executed_path_months"],
+                          "series_passes": [list(g) for g in sim.last_series_plan], "result": summary}))
     if world > 1:
         dist.destroy_process_group()
 

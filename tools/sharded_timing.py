@@ -43,7 +43,7 @@ pool = torch.zeros(len(specs) * 8192, dtype=torch.int64, device="cuda")
 t_ar_pool = timed(lambda: sim.coll.sum_(pool), reps=20)
 small = torch.zeros(7, dtype=torch.float64, device="cuda"); hists = torch.zeros(160, dtype=torch.int64, device="cuda")
 t_hist = timed(lambda: sim._final_balance_histograms(b, small[3:5], small[5:7], hists), reps=10)
-t_agree = timed(lambda: sim._agree(False), reps=10)
+t_agree = timed(lambda: sim._agree_min(1), reps=10)
 t_tl = timed(lambda: sim.run_batch_device(240, n, first_path=dist.get_rank() * n))
 h = torch.zeros(len(specs) * 32 * 256, dtype=torch.int32, device="cuda")
 t_ar = timed(lambda: sim.coll.sum_(h), reps=20)
