@@ -64,18 +64,47 @@ def _silence_logs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML from a thread every 10 ms
+    (a timed region of ten 9-ms steps is shorter than one `nvidia-smi` start-up on an 8-GPU box);
+    `nvidia-smi -lms` is the fallback when the NVML binding is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.handle = None
+        self.samples = []
+        self.bits = 0
+        self.stop_flag = threading.Event()
+        self.thread = None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber devices: go through the UUID
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, handle
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -85,11 +114,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(self.handle))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            names = sorted(name for bit, name in self.REASON_BITS.items() if self.bits & bit)
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.samples), "reasons": names, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -113,7 +159,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # -------------------------------------------------------------------------------------------------
