@@ -340,6 +340,8 @@ class Context:
 
         arr_np = specs if hasattr(specs, "dtype") else self.select_rows(specs)
         n_rows = len(arr_np)
+        if n_rows == 0:
+            return None
         arr = C.cast(arr_np.ctypes.data, C.POINTER(SelectRow))
         if all_reduce is None:
             self._check(self.lib.mcr_quantiles_rows(self.handle, arr, n_rows, _ptr(out), _ptr(counts), _stream_handle()))

@@ -80,7 +80,27 @@ def _worker(rank, world, port, out_dir):
         lo, cnt = shard_range(1001, rank, world)
         assert all(c[1] == cnt and c[2] == lo for c in calls)   # each rank evaluated only its own shard
         assert sim.last_search_stats["launches"] <= 3
-        torch.save({"months": months, "prob": prob, "curve": curve, "events": events},
+        # planning hooks of the sharded aggregate path: every rank must plan with the same numbers
+        sim._torch_device = lambda: torch.device("cpu")
+        assert sim._agree_min(1000 + 50 * rank, key="budget") == 1000       # minimum over ranks ...
+        assert sim._agree_min(5, key="budget") == 1000                      # ... remembered per call shape
+        free = (100 + 40 * rank) * 10 ** 9                                   # rank 1 has more free HBM
+        torch.cuda.mem_get_info = lambda device=None: (free, 180 * 10 ** 9)
+        n, T, R = 125_000_000, 71, 50                                        # config #5 shard: 71 + 71 + 50 GB
+        plan = sim._series_plan(n, T, R, True, key=("c5",))
+        assert plan == [("traj",), ("real",), ("wr",)]                      # 70 % of the SMALLER 100 GB holds one series
+        assert sim._series_plan(1_000_000, 61, 40, True, key=("c3",)) == [("traj", "real", "wr")]
+        assert sim._series_plan(n, T, R, False, key=("none",)) == [()]
+        # deferred check of the pooled select: a non-zero "could not finish" count rejects the step once
+        assert sim._selects_ok()
+        sim._select_flag = torch.tensor([0])
+        assert sim._selects_ok() and sim._select_flag is None
+        sim._select_flag = torch.tensor([2])
+        assert not sim._selects_ok() and sim._selects_ok()
+        with sim._stepwise_selects():
+            assert sim._stepwise_only
+        assert not sim._stepwise_only
+        torch.save({"months": months, "prob": prob, "curve": curve, "events": events, "plan": plan},
                    os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
