@@ -187,14 +187,19 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
                     int32_t n_months, mcr_path_record* record_host, double* trajectory_host,
                     double* real_trajectory_host, double* wr_host);
 
-/* Device evaluation of the three private helpers the reference tests call directly
- * (backend/simulation.py:201-254, :256-272, :274-359). One strict thread each. */
+/* Device evaluation of the private helpers of the path (backend/simulation.py:201-254,
+ * :256-272, :274-359 — the three the reference tests call directly — and :361-450). One strict
+ * thread each. */
 int mcr_helper_withdraw(mcr_ctx* ctx, double bal, double cost_basis, double net_target,
                         int32_t use_real_tax, double real_tax_rate, double out4_host[4]);
 int mcr_helper_net_liquidation(mcr_ctx* ctx, double bal, double cost_basis, int32_t use_real_tax,
                                double real_tax_rate, double* out_host);
 int mcr_helper_rebalance(mcr_ctx* ctx, double bal1, double cb1, double bal2, double cb2,
                          double out4_host[4]);
+/* `_apply_annual_gain_taxes` (backend/simulation.py:361-450): out5 = {bal1, cb1, bal2, cb2,
+ * tax_failed (0.0 / 1.0)} after the period's mark-to-market tax and the trailing rebalance. */
+int mcr_helper_annual_tax(mcr_ctx* ctx, double bal1, double cb1, double bal2, double cb2,
+                          double gain1, double gain2, double out5_host[5]);
 
 /* Native shocks in the replay layout: shocks_dev[(m*3 + c) * shocks_ld + i] for global paths
  * first_path + i — the device analogue of `_draw_shock_path` (backend/simulation.py:452-466).

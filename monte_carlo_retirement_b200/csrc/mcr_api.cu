@@ -379,13 +379,13 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
 }
 
 static int run_helper(mcr_ctx* ctx, int which, double a, double b, double c, double d, int use_tax, double rate,
-                      double* out_host, int n_out) {
+                      double* out_host, int n_out, double e = 0.0) {
   if (!ctx || !out_host) return fail(ctx, MCR_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
   if (int rc = ensure_scratch(ctx, 64)) return rc;
-  MCR_CUDA(ctx, strict_launchers().helper(ctx->dev, which, a, b, c, d, use_tax, rate, (double*)ctx->scratch, 0));
+  MCR_CUDA(ctx, strict_launchers().helper(ctx->dev, which, a, b, c, d, use_tax, rate, e, (double*)ctx->scratch, 0));
   ctx->launches += 1;
   MCR_CUDA(ctx, cudaMemcpy(out_host, ctx->scratch, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost));
   return MCR_OK;
@@ -403,6 +403,11 @@ int mcr_helper_net_liquidation(mcr_ctx* ctx, double bal, double cost_basis, int3
 
 int mcr_helper_rebalance(mcr_ctx* ctx, double bal1, double cb1, double bal2, double cb2, double out4_host[4]) {
   return run_helper(ctx, 2, bal1, cb1, bal2, cb2, 0, 0.0, out4_host, 4);
+}
+
+int mcr_helper_annual_tax(mcr_ctx* ctx, double bal1, double cb1, double bal2, double cb2, double gain1, double gain2,
+                          double out5_host[5]) {
+  return run_helper(ctx, 3, bal1, cb1, bal2, cb2, 0, gain1, out5_host, 5, gain2);
 }
 
 int mcr_draw_shocks(mcr_ctx* ctx, int seed_stream, int64_t first_path, int64_t n_paths, int32_t n_months,

@@ -41,7 +41,7 @@ struct Launchers {
   cudaError_t (*draw)(const DevParams&, const PhiloxKeys& keys, uint32_t seed_stream, int64_t first_path,
                       int64_t n_paths, int32_t n_months, double* shocks, int64_t ld, cudaStream_t);
   cudaError_t (*helper)(const DevParams&, int which, double a, double b, double c, double d, int use_tax,
-                        double rate, double* out, cudaStream_t);
+                        double rate, double e, double* out, cudaStream_t);
 };
 
 const Launchers& strict_launchers();

@@ -136,7 +136,7 @@ __global__ void k_draw_shocks(const __grid_constant__ DevParams P, const __grid_
 // One-thread helper evaluations (strict build only is exported)
 template <bool FAST>
 __global__ void k_helper(const __grid_constant__ DevParams P, int which, double a, double b, double c, double d,
-                         int use_tax, double rate, double* out) {
+                         int use_tax, double rate, double e, double* out) {
   if (threadIdx.x || blockIdx.x) return;
   if (which == 0) {  // withdraw(bal=a, cb=b, target=c)
     double gross, net;
@@ -145,9 +145,12 @@ __global__ void k_helper(const __grid_constant__ DevParams P, int which, double 
     out[0] = a; out[1] = b; out[2] = gross; out[3] = net;
   } else if (which == 1) {  // net liquidation
     out[0] = net_liq(a, b, use_tax && rate > 0, rate);
-  } else {  // rebalance(b1=a, cb1=b, b2=c, cb2=d)
+  } else if (which == 2) {  // rebalance(b1=a, cb1=b, b2=c, cb2=d)
     rebalance<FAST, true>(P, a, b, c, d);
     out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+  } else {  // annual tax(b1=a, cb1=b, b2=c, cb2=d, gain1=rate, gain2=e)
+    const bool failed = annual_tax<FAST, true>(P, a, b, c, d, rate, e);
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d; out[4] = failed ? 1.0 : 0.0;
   }
 }
 
@@ -208,8 +211,8 @@ static cudaError_t launch_draw(const DevParams& P, const PhiloxKeys& keys, uint3
 }
 
 static cudaError_t launch_helper(const DevParams& P, int which, double a, double b, double c, double d, int use_tax,
-                                 double rate, double* out, cudaStream_t st) {
-  k_helper<MCR_FAST != 0><<<1, 32, 0, st>>>(P, which, a, b, c, d, use_tax, rate, out);
+                                 double rate, double e, double* out, cudaStream_t st) {
+  k_helper<MCR_FAST != 0><<<1, 32, 0, st>>>(P, which, a, b, c, d, use_tax, rate, e, out);
   return cudaGetLastError();
 }
 

@@ -134,6 +134,7 @@ SIGNATURES = {
     "mcr_helper_withdraw": (C.c_int, [_VP, _D, _D, _D, _I32, _D, C.POINTER(_D)]),
     "mcr_helper_net_liquidation": (C.c_int, [_VP, _D, _D, _I32, _D, C.POINTER(_D)]),
     "mcr_helper_rebalance": (C.c_int, [_VP, _D, _D, _D, _D, C.POINTER(_D)]),
+    "mcr_helper_annual_tax": (C.c_int, [_VP, _D, _D, _D, _D, _D, _D, C.POINTER(_D)]),
     "mcr_draw_shocks": (C.c_int, [_VP, C.c_int, _I64, _I64, _I32, _U32, _VP, _I64, _VP]),
     "mcr_search_batch": (C.c_int, [_VP, C.c_int, C.POINTER(_I32), _I32, _I64, _I64, _U32, _VP, _VP, _VP]),
     "mcr_quantiles": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, C.POINTER(_D), _I32, _U32, _VP, _VP, _VP]),
@@ -270,6 +271,11 @@ class Context:
         out = (_D * 4)()
         self._check(self.lib.mcr_helper_rebalance(self.handle, b1, cb1, b2, cb2, out))
         return tuple(out)
+
+    def helper_annual_tax(self, b1, cb1, b2, cb2, gain1, gain2):
+        out = (_D * 5)()
+        self._check(self.lib.mcr_helper_annual_tax(self.handle, b1, cb1, b2, cb2, gain1, gain2, out))
+        return out[0], out[1], out[2], out[3], bool(out[4])
 
     def draw_shocks(self, seed_stream: int, first_path: int, n_paths: int, n_months: int, shocks, shocks_ld: int,
                     strict: bool = False) -> None:

@@ -360,6 +360,13 @@ class RetirementMonteCarloSimulator:
         """simulation.py:274-359."""
         return self.native_context.helper_rebalance(float(bal_inv1), float(cb_inv1), float(bal_inv2), float(cb_inv2))
 
+    def _apply_annual_gain_taxes(self, balance_inv1: float, cost_basis_inv1: float, balance_inv2: float,
+                                 cost_basis_inv2: float, gain_inv1: float,
+                                 gain_inv2: float) -> Tuple[float, float, float, float, bool]:
+        """simulation.py:361-450."""
+        return self.native_context.helper_annual_tax(float(balance_inv1), float(cost_basis_inv1), float(balance_inv2),
+                                                     float(cost_basis_inv2), float(gain_inv1), float(gain_inv2))
+
     # ---- one path (simulation.py:476-950) ----------------------------------------------------
     def _run_single_simulation_path(self, working_months: int, path_seed: int) -> Dict[str, Union[float, List[float]]]:
         p = self.params_model

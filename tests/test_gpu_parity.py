@@ -115,6 +115,24 @@ def test_helpers_bit_exact_vs_reference():
             assert np.array_equal(np.array(got), exp), (name, row, got, exp)
 
 
+def test_annual_tax_helper_bit_exact_vs_reference():
+    """_apply_annual_gain_taxes (simulation.py:361-450) as one strict CUDA thread: balances, cost
+    bases and the tax_failed flag of the reference on random inputs, for scenarios with annual
+    tax on one asset, on both, and on none (where only the trailing rebalance acts)."""
+    z = golden_io.load_helpers()
+    cfgs = {"tax_heavy": scenarios.TAX_HEAVY, "config_json": scenarios.CONFIG_JSON,
+            "annual_both": scenarios.ANNUAL_BOTH, "test_base": scenarios.TEST_BASE}
+    failed_seen = 0
+    for name in z["sim_names"]:
+        s = make_sim(cfgs[str(name)])
+        for row, exp in zip(z["rb_in"][::2], z[f"at_{name}"][::2]):
+            got = s._apply_annual_gain_taxes(*[float(v) for v in row[:6]])
+            assert isinstance(got[4], bool)
+            assert np.array_equal(np.array([*got[:4], float(got[4])]), exp), (name, row, got, exp)
+            failed_seen += int(got[4])
+    assert failed_seen > 0  # the fixture exercises the tax_failed branch
+
+
 @pytest.mark.parametrize("name,cfg,seed,case", CASES[1::4], ids=IDS[1::4])
 def test_dropin_7tuple_numpy_rng_matches_reference(name, cfg, seed, case):
     """run_monte_carlo_simulations with rng='numpy' against the reference's own 7-tuple: device
