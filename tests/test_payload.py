@@ -205,3 +205,85 @@ def test_cli_report_from_aggregates_equals_reference_log_and_histogram(name):
     fig = report.figure_result_lines(cfg, g["working_months"], agg)
     assert fig[0] == "--- Results ---" and fig[1].startswith(f"Req.Work: {g['working_months']}mo")
     assert report.histogram_label(agg) == f"Successful Outcomes ({agg['success_probability']:.1f}%)"
+
+
+# ---- the reference's own API tests, restated against payload.build_result -------------------------
+def test_outcomes_keep_success_flags_and_zero_balance_median():
+    """tests/test_simulation_correctness.py:737-778 of the reference: the histogram cohort is the
+    backend's successful-path cohort (a successful path may finish at exactly 0)."""
+    import pandas as pd
+
+    cfg = Config(**dict(__import__("scenarios").TEST_BASE, num_simulations_main=3, retirement_years=1,
+                        other_income_streams=[]))
+    summary = pd.DataFrame({
+        "Start Balance": [100.0, 100.0, 100.0], "Final Balance": [0.0, 50.0, 25.0], "Success": [True, True, False],
+        "YearsToRuin": [float("nan"), float("nan"), 0.5], "First Year Gross Withdrawal": [0.0, 10.0, 10.0],
+        "First Year Real Gross Withdrawal": [0.0, 10.0, 10.0], "Inflation At Retirement": [1.0, 1.0, 1.0]})
+
+    class FakeSimulator:
+        def run_monte_carlo_simulations(self, **_kwargs):
+            return summary, None, None, None, None, None, None
+
+    result = payload.build_result(cfg, FakeSimulator(), required_w_months=0, search_curve=[])
+    _validate_with_reference_model(result)
+    assert result["summary"]["success_probability"] == pytest.approx(66.67)
+    assert result["summary"]["median_final_balance_successful"] == pytest.approx(25.0)
+    assert result["histogram"]["final_balances"] == [0.0, 50.0, 25.0]
+    assert result["histogram"]["success_flags"] == [True, True, False]
+    assert result["ruin_histogram"]["failure_count"] == 1
+    assert result["ruin_histogram"]["years_to_ruin"] == [0.5]
+    assert result["trajectory"] is None and result["withdrawal_rate"] is None and result["search_curve"] is None
+
+
+def test_payload_preserves_exact_fractional_timeline():
+    """tests/test_simulation_correctness.py:781-817: a 13-month working period stays 13/12 years."""
+    import scenarios
+
+    d = dict(scenarios.TEST_BASE, num_simulations_main=2, retirement_years=1, monthly_expenses=0.0, seed=5)
+    cfg = Config(**d)
+    result = payload.build_result(cfg, OracleBackedSimulator(d), required_w_months=13,
+                                  search_curve=[{"working_months": 13, "working_years": 1.1, "probability": 100.0}])
+    _validate_with_reference_model(result)
+    ret = 13 / 12
+    assert result["trajectory"]["years"] == pytest.approx([0.0, 1.0, ret, ret + 1])
+    assert result["withdrawal_rate"]["years"][0] == pytest.approx(ret)
+    assert result["reference_lines"][0]["year"] == pytest.approx(ret)
+    assert result["summary"]["working_period_is_estimate"] is True
+
+
+def _validate_with_reference_model(result) -> None:
+    """`SimulationResponse.model_validate` with the reference's own pydantic model — only where the
+    reference tree is mounted (the build container); the golden payloads were validated with it
+    when they were generated (tests/golden/make_payload_golden.py)."""
+    import sys
+
+    backend = "/root/reference/backend"
+    if not os.path.isdir(backend):
+        return
+    saved_path, saved_mods = list(sys.path), {k: sys.modules.get(k) for k in ("server", "config", "constants", "simulation", "utils")}
+    sys.path.insert(0, backend)
+    try:
+        for k in saved_mods:
+            sys.modules.pop(k, None)
+        import server  # the reference's FastAPI module (no app is started)
+
+        server.SimulationResponse.model_validate(result)
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved_mods.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+
+
+def test_aggregate_shaped_payload_validates_against_the_reference_response_model():
+    """The aggregate-only payload keeps every field the reference model requires (the O(N) lists
+    stay present and empty; `binned` / `bins` are extra keys)."""
+    g = GOLDEN["stressed"]
+    legacy = json.loads(json.dumps(g["result"]))
+    legacy["histogram"] = {"final_balances": [], "start_balances": [], "success_flags": [],
+                           "binned": payload.balance_bins(0.0, 1.0, [0] * 60, 0.0, 0, 10)}
+    legacy["ruin_histogram"] = {"years_to_ruin": [], "failure_count": 3, "total_paths": 10,
+                                "bins": payload.ruin_year_bins([0, 1, 0, 2])}
+    _validate_with_reference_model(legacy)
+    assert legacy["ruin_histogram"]["bins"] == [{"year": 1, "label": "1", "count": 3}]
