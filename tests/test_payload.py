@@ -287,3 +287,60 @@ def test_aggregate_shaped_payload_validates_against_the_reference_response_model
                                 "bins": payload.ruin_year_bins([0, 1, 0, 2])}
     _validate_with_reference_model(legacy)
     assert legacy["ruin_histogram"]["bins"] == [{"year": 1, "label": "1", "count": 3}]
+
+
+# ---- aggregate-only assembly on the CPU: a stub that answers run_aggregates() from the oracle -------
+class OracleAggregates(OracleBackedSimulator):
+    """`run_aggregates` (the dict DeviceAggregates.to_host returns) reduced on the host from the
+    oracle's 7-tuple, so that payload's aggregate mode can be checked without a GPU."""
+
+    def run_aggregates(self, working_months, num_simulations, *, bands=True, samples=False, first_path=0):
+        summary, traj, smp, wr, real, real_smp, wr_counts = self.sim.run(working_months, num_simulations)
+        agg = host_aggregates(summary)
+        ok = summary["Success"].astype(bool)
+        succ = summary.loc[ok, "Final Balance"].to_numpy()
+        if len(succ) and succ.max() > succ.min():
+            lo, hi = float(succ.min()), float(succ.max())
+            width = (hi - lo) / 60
+            counts = np.bincount(np.minimum(np.floor((succ - lo) / width), 59).astype(int), minlength=60).tolist()
+        elif len(succ):
+            lo = hi = float(succ.min())
+            counts = [len(succ)] + [0] * 59
+        else:
+            lo = hi = float("nan")
+            counts = [0] * 60
+        months = np.rint(summary.loc[~ok, "YearsToRuin"].dropna().to_numpy() * 12).astype(int)
+        R = len(wr)
+        agg.update({
+            "final_balance_hist_60": {"range": [lo, hi], "counts": counts},
+            "ruin_month_hist": np.bincount(months, minlength=12 * R + 1).tolist(),
+            "trajectory_bands": traj, "real_trajectory_bands": real, "withdrawal_rate_bands": wr,
+            "withdrawal_rate_counts": wr_counts, "sample_paths": smp, "real_sample_paths": real_smp,
+        })
+        return agg
+
+
+@pytest.mark.parametrize("name", ["config_json", "jorge_plus", "stressed", "broke"])
+def test_aggregate_mode_assembles_the_legacy_payload_without_the_lists(name):
+    g = GOLDEN[name]
+    cfg = Config(**g["cfg"])
+    wm, curve = g["working_months"], g["search_curve"]
+    legacy = payload.build_result(cfg, OracleAggregates(g["cfg"]), wm, search_curve=curve, mode="legacy")
+    agg = payload.build_result(cfg, OracleAggregates(g["cfg"]), wm, search_curve=curve, mode="aggregate")
+    assert agg.keys() == legacy.keys()
+    for key in ("scenario", "summary", "trajectory", "trajectory_real", "withdrawal_rate", "search_curve",
+                "reference_lines"):
+        assert json.dumps(agg[key], sort_keys=True) == json.dumps(legacy[key], sort_keys=True), key
+    assert agg["histogram"]["final_balances"] == [] and agg["ruin_histogram"]["years_to_ruin"] == []
+    assert agg["ruin_histogram"]["failure_count"] == legacy["ruin_histogram"]["failure_count"]
+    assert agg["ruin_histogram"]["bins"] == js_bin_ruin_years(legacy["ruin_histogram"]["years_to_ruin"])
+    summary = OracleAggregates(g["cfg"]).run_monte_carlo_simulations(wm, cfg.num_simulations_main)[0]
+    want = js_bin_data(summary["Final Balance"].tolist(), summary["Success"].tolist())
+    got = agg["histogram"]["binned"]
+    assert got["successRate"] == want["successRate"] and got["median"] == want["median"]
+    assert [b["count"] for b in got["bins"]] == [b["count"] for b in want["bins"]]
+    assert [b["label"] for b in got["bins"]] == [b["label"] for b in want["bins"]]
+    _validate_with_reference_model(json.loads(json.dumps(agg, allow_nan=False)))
+    # "auto" picks the aggregate path above the threshold when the simulator offers it
+    auto = payload.build_result(cfg, OracleAggregates(g["cfg"]), wm, search_curve=curve, aggregate_threshold=1)
+    assert auto["histogram"]["final_balances"] == []
