@@ -105,6 +105,16 @@ def test_oracle_equals_reference_on_random_scenarios(block):
                 if key == "Success":
                     continue
                 assert _same(got[key], want[key]), (key, cfg, wm, seed, got[key], want[key])
+        # the aggregated 7-tuple (seed spawning for a NEW n, pandas quantiles, sampled columns, WR counts)
+        if k % 3 == 0:
+            w = ref.run_monte_carlo_simulations(wm, 7)
+            g = mine.run(wm, 7)
+            assert list(g[0].columns) == list(w[0].columns)
+            for col in w[0].columns:
+                assert _same(g[0][col].to_numpy(dtype=float), w[0][col].to_numpy(dtype=float)), (col, cfg, wm)
+            for i in (1, 3, 4):
+                assert list(g[i].columns) == list(w[i].columns) and _same(g[i].to_numpy(), w[i].to_numpy()), (i, cfg, wm)
+            assert _same(g[2], w[2]) and _same(g[5], w[5]) and g[6] == w[6]
         # the helpers on this scenario's parameters
         b = rng.uniform(0, 1e6, 4)
         assert _same(orc.rebalance(mine.p, *b), ref._rebalance_portfolio(*[float(v) for v in b]))
