@@ -206,3 +206,21 @@ def test_search_driver_replays_reference_decisions_and_events(name):
     months, prob, curve = sim.find_minimum_working_months(verbose=False, progress_callback=events.append)
     assert months == g["months"] and prob == g["prob"] and curve == g["curve"]
     assert events == g["events"]
+
+
+def test_header_is_a_plain_c_header(tmp_path):
+    """include/mcr.h is the drop-in boundary: it must be consumable from C (cgo / ctypes / FFI
+    generators), not only from the C++ that implements it."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mcr.h"\nint main(void) { mcr_params p; mcr_outputs o; (void)p; (void)o; '
+                   'return (int)sizeof(mcr_path_record) == 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
