@@ -400,7 +400,12 @@ def run_b200_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "paths_per_gpu": n, "months": months,
                        "l2": "no HBM inputs (counter-based Philox); each step writes 1.36 GB of outputs, > 126 MB L2",
-                       "success_probability": host["success_probability"]},
+                       "success_probability": host["success_probability"],
+                       # N > 1: times the pooled distributed select gave up on a row and the step was
+                       # re-run with the stepwise protocol (checked after the timed loop; 0 = the timed
+                       # steps are the whole work)
+                       "select_fallbacks": int(getattr(sim, "select_fallbacks", 0)),
+                       "pipeline": bool(args.pipeline)},
             "roofline": {
                 "bound": "fp64_pipe", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "Tslot/s",
                 "frac": achieved / fp64_peak,

@@ -100,6 +100,7 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         self._agreed: Dict[Any, int] = {}
         self._select_flag = None
         self._stepwise_only = False
+        self.select_fallbacks = 0
         self._sign4 = None
         if self.rng_mode != "philox":
             raise ValueError("sharding needs the counter-based Philox draws (rng='philox')")
@@ -146,7 +147,10 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
 
     def _selects_ok(self) -> bool:
         flag, self._select_flag = self._select_flag, None
-        return flag is None or int(flag.item()) == 0
+        ok = flag is None or int(flag.item()) == 0
+        if not ok:
+            self.select_fallbacks += 1  # reported by bench.py: a fallback re-runs work outside a timed loop
+        return ok
 
     def _stepwise_selects(self):
         import contextlib

@@ -97,6 +97,7 @@ def _worker(rank, world, port, out_dir):
         assert sim._selects_ok() and sim._select_flag is None
         sim._select_flag = torch.tensor([2])
         assert not sim._selects_ok() and sim._selects_ok()
+        assert sim.select_fallbacks == 1
         with sim._stepwise_selects():
             assert sim._stepwise_only
         assert not sim._stepwise_only
