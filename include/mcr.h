@@ -53,6 +53,16 @@ extern "C" {
                                 use it. Without it the fast arithmetic is used (same
                                 formulas, FMA contraction + shared reciprocals, <=1e-12 rel). */
 
+#define MCR_FLAG_SMALL_RETURNS 0x2u /* mcr_replay without MCR_FLAG_STRICT only: the caller has
+                                verified on the host that |mu_log/12 + sigma_log/sqrt(12) * z| <
+                                mcr_small_returns_bound(ctx) for every supplied shock of all three
+                                factors — the bound mcr_create proved for this scenario's OWN
+                                Philox draws. The fast build then runs the SAME kernel variant as
+                                native-draw launches (short exp polynomial, lean month steps) on
+                                the supplied draws, which is how the tests hold the benchmarked
+                                variant to the <= 1e-9 replay contract. Ignored when the bound is
+                                0; behaviour is undefined if the guarantee does not hold. */
+
 /* seed streams — backend/simulation.py:147-151,177-185 (search vs final SeedSequence children) */
 #define MCR_STREAM_SEARCH 0
 #define MCR_STREAM_FINAL 1
@@ -148,6 +158,9 @@ int mcr_create(const mcr_params* params, uint64_t main_seed, int device, mcr_ctx
 int mcr_destroy(mcr_ctx* ctx);
 const char* mcr_last_error(const mcr_ctx* ctx);
 int mcr_abi_version(void);
+/* 0.05 / 0.1: every monthly log-return of this scenario's native draws is provably below it
+ * (Box-Muller normals of 32-bit uniforms are bounded by 6.77); 0: no such bound. */
+double mcr_small_returns_bound(const mcr_ctx* ctx);
 
 /* ---- host-side pure helpers (a2/a3 of SURVEY §8) -------------------------------------- */
 
@@ -312,6 +325,11 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
 int mcr_first_year_rates(mcr_ctx* ctx, const double* start_dev, const double* first_year_real_dev,
                          int64_t n, double* rates_dev, void* stream);
 
+/* years[i] = ruin_month[i] / 12.0 (IEEE division), NaN where ruin_month[i] < 0: the "YearsToRuin"
+ * column of summary_df (backend/simulation.py:825-828,943,1018) filled on the device. */
+int mcr_years_to_ruin(mcr_ctx* ctx, const int32_t* ruin_month_dev, int64_t n, double* years_dev,
+                      void* stream);
+
 #define MCR_HIST_NUMPY 0 /* numpy.histogram / matplotlib plt.hist(bins=n) — plotting.py:46-59  */
 #define MCR_HIST_FLOOR 1 /* idx = min(floor((v-min)/width), n-1) — HistogramChart.jsx:13-60   */
 
@@ -338,6 +356,13 @@ int mcr_gather_columns(mcr_ctx* ctx, const double* series_dev, int64_t ld, int32
 /* DFMA-chain microbenchmark: FP64-pipe issue slots (lane-instructions) per second on this
  * device — the roofline denominator of SURVEY §8d. Synchronises. */
 int mcr_fp64_peak_slots_per_s(mcr_ctx* ctx, double* slots_per_s_host);
+
+/* Which compile-time specialisation the last mcr_simulate / mcr_replay / mcr_search_batch of this
+ * context launched: 0 generic, 1 both assets taxed on realized gains, 2 no tax bites; +2 / +4 for
+ * the fast build's bounded-return variants (< 0.1 / < 0.05: short exp polynomial + lean month
+ * steps). -1 before the first launch. Lets the tests assert that the variant bench.py times is the
+ * one their parity checks ran. */
+int32_t mcr_last_variant(const mcr_ctx* ctx);
 
 /* Kernels launched by this context so far (the `gpu_launches` claim of bench.py). */
 int64_t mcr_launch_count(const mcr_ctx* ctx);

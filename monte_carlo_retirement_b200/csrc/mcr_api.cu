@@ -5,10 +5,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
 
+#include "mcr_derive.h"
 #include "mcr_internal.h"
 #include "mcr_path.cuh"
 #include "mcr_reduce.h"
@@ -26,12 +28,22 @@ struct mcr_ctx {
   std::mutex mu;
   std::string err;
   int64_t launches = 0;
+  int last_variant = -1;   // pick_cfg_index() of the last timeline / search launch
   // live (positive-amount) streams in original order: eligibility age and duration in months
   double live_start_age[MCR_MAX_STREAMS];
   int32_t live_duration[MCR_MAX_STREAMS];
-  // scratch (device), grown on demand
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
+  // Scratch (device), grown on demand. One buffer PER STREAM: calls that run on different streams
+  // (aggregates_device(pipeline=True) puts the selects on a side stream while the next search /
+  // single-path call is enqueued on the main one) never share live scratch. A buffer is only
+  // replaced after its own stream has drained.
+  struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+  };
+  std::map<cudaStream_t, Scratch> scratch;
+  // private non-blocking stream of the synchronous host-output entry points (single path,
+  // helpers, peak): they must not serialise against other contexts through the legacy stream
+  cudaStream_t own_stream = nullptr;
 };
 
 static thread_local std::string g_tls_err;
@@ -66,107 +78,35 @@ int cuda_fail(mcr_ctx* ctx, cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
   } while (0)
 
-uint64_t splitmix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-
-int ensure_scratch(mcr_ctx* ctx, size_t bytes) {
-  if (bytes <= ctx->scratch_bytes) return MCR_OK;
-  if (ctx->scratch) cudaFree(ctx->scratch);
-  ctx->scratch = nullptr;
-  ctx->scratch_bytes = 0;
-  size_t want = bytes < (1u << 16) ? (1u << 16) : bytes;
-  if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) {
-    cudaGetLastError();
-    return fail(ctx, MCR_ENOMEM, "scratch allocation of " + std::to_string(want) + " bytes failed");
+// scratch of at least `bytes` for work enqueued on `st` (see mcr_ctx::scratch)
+int ensure_scratch(mcr_ctx* ctx, cudaStream_t st, size_t bytes, void** out) {
+  mcr_ctx::Scratch& s = ctx->scratch[st];
+  if (bytes > s.bytes) {
+    if (s.p) {
+      // work already enqueued on this stream may still read the old buffer
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize(scratch growth)");
+      cudaFree(s.p);
+    }
+    s.p = nullptr;
+    s.bytes = 0;
+    const size_t want = bytes < (1u << 16) ? (1u << 16) : bytes;
+    if (cudaMalloc(&s.p, want) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, MCR_ENOMEM, "scratch allocation of " + std::to_string(want) + " bytes failed");
+    }
+    s.bytes = want;
   }
-  ctx->scratch_bytes = want;
+  *out = s.p;
   return MCR_OK;
 }
 
-// stream_payment_start_month_index — simulation.py:47-63, same double operations as CPython
-int32_t start_month_index(double current_age, int32_t wm, double start_at_age) {
-  const double ret = current_age + (double)wm / (double)MCR_MONTHS_PER_YEAR;
-  const double elig = (start_at_age > ret) ? start_at_age : ret;
-  const double k = std::ceil((elig - ret) * (double)MCR_MONTHS_PER_YEAR - MCR_SMALL_EPSILON);
-  if (!(k > 0)) return 0;
-  return k > 2147483647.0 ? 2147483647 : (int32_t)k;
-}
-
-int validate_and_derive(const mcr_params& p, DevParams& d, double* live_start_age, int32_t* live_duration,
-                        std::string& why) {
-  auto bad = [&](const char* m) { why = m; return MCR_EINVAL; };
-  if (!(p.initial_balance >= 0) || !(p.monthly_contribution >= 0) || !(p.monthly_expenses >= 0))
-    return bad("balances, contributions and expenses must be >= 0");
-  if (!(p.contribution_growth_rate_annual >= 0)) return bad("contribution_growth_rate_annual must be >= 0");
-  if (!(p.allocation_inv1_pct >= 0 && p.allocation_inv1_pct <= 1)) return bad("allocation_inv1_pct must be in [0,1]");
-  if (p.retirement_years <= 0) return bad("retirement_years must be > 0");
-  if (p.retirement_years > 1000) return bad("retirement_years above 1000 is not supported");
-  if (p.n_streams < 0 || p.n_streams > MCR_MAX_STREAMS)
-    return bad("at most 16 other_income_streams are supported by the CUDA engine");
-  if (!(p.inv1_sigma_log >= 0) || !(p.inf_sigma_log >= 0) || !(p.prem_sigma_log >= 0)) return bad("negative sigma_log");
-  if (!(p.equity_inflation_rho >= -1 && p.equity_inflation_rho <= 1)) return bad("correlation must be in [-1,1]");
-  const double rates[4] = {p.inv1_annual_tax_on_gains_rate, p.inv1_realized_gains_tax_rate,
-                           p.inv2_annual_tax_on_gains_rate, p.inv2_realized_gains_tax_rate};
-  for (double r : rates)
-    if (!(r >= 0 && r <= 1)) return bad("tax rates must be in [0,1]");
-  std::memset(&d, 0, sizeof(d));
-  d.B0 = p.initial_balance;
-  d.C0 = p.monthly_contribution;
-  d.growth1p = 1 + p.contribution_growth_rate_annual;            // simulation.py:517
-  d.E = p.monthly_expenses;
-  d.a1 = p.allocation_inv1_pct;
-  d.a2 = 1.0 - p.allocation_inv1_pct;                            // config.py:124-126
-  const double mpy = (double)MCR_MONTHS_PER_YEAR;
-  const double root = std::sqrt(mpy);
-  d.mu1 = p.inv1_mu_log / mpy;  d.sg1 = p.inv1_sigma_log / root; // simulation.py:472-474
-  d.muI = p.inf_mu_log / mpy;   d.sgI = p.inf_sigma_log / root;
-  d.muP = p.prem_mu_log / mpy;  d.sgP = p.prem_sigma_log / root;
-  d.rho = p.equity_inflation_rho;
-  const double c2 = 1.0 - d.rho * d.rho;
-  d.rho_c = std::sqrt(c2 > 0.0 ? c2 : 0.0);                      // simulation.py:463
-  d.rho_f = (float)d.rho;
-  d.rho_c_f = (float)d.rho_c;
-  d.rate1 = p.inv1_realized_gains_tax_rate;
-  d.rate2 = p.inv2_realized_gains_tax_rate;
-  d.ann1 = p.inv1_annual_tax_on_gains_rate;
-  d.ann2 = p.inv2_annual_tax_on_gains_rate;
-  d.use1 = p.inv1_use_realized_gains_tax_system != 0;
-  d.use2 = p.inv2_use_realized_gains_tax_system != 0;
-  d.taxed1 = d.use1 && d.rate1 > 0;
-  d.taxed2 = d.use2 && d.rate2 > 0;
-  d.growth_on = p.contribution_growth_rate_annual > 0;
-  d.algebra_ok = (d.taxed1 || d.taxed2) && (!d.taxed1 || d.rate1 <= 0.999) && (!d.taxed2 || d.rate2 <= 0.999);
-  d.annual_any = (!d.use1 && d.ann1 > 0) || (!d.use2 && d.ann2 > 0);
-  {
-    // |mu/12| + sigma/sqrt(12) * z_max for the three factors; Box-Muller on 32-bit uniforms
-    // gives |n| <= sqrt(-2 ln 2^-33) = 6.77, the inflation shock is rho*n0 + rho_c*n1
-    const double zmax = 6.8, zinf = zmax * (std::fabs(d.rho) + d.rho_c);
-    const double b1 = std::fabs(d.mu1) + d.sg1 * zmax, bi = std::fabs(d.muI) + d.sgI * zinf,
-                 bp = std::fabs(d.muP) + d.sgP * zmax;
-    d.exp_small = (b1 < 0.1 && bi < 0.1 && bp < 0.1) ? 1 : 0;
+int own_stream(mcr_ctx* ctx, cudaStream_t* st) {
+  if (!ctx->own_stream) {
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamCreateWithFlags");
   }
-  d.R = p.retirement_years;
-  int live = 0;
-  for (int k = 0; k < p.n_streams; ++k) {
-    const mcr_income_stream& s = p.streams[k];
-    if (!(s.monthly_amount_today >= 0) || !(s.tax_rate >= 0 && s.tax_rate <= 1) || !(s.start_at_age >= 0))
-      return bad("bad other_income_streams entry");
-    // a zero amount pays nominal 0.0 and adds +0.0 to the income sum (exact); a zero duration
-    // is never active (simulation.py:653-656): neither can change any result.
-    if (s.monthly_amount_today == 0.0 || s.duration_years == 0) continue;
-    d.streams[live].amount = s.monthly_amount_today;
-    d.streams[live].net_factor = 1.0 - s.tax_rate;               // simulation.py:675-677
-    d.streams[live].duration = s.duration_years < 0 ? -1 : s.duration_years * MCR_MONTHS_PER_YEAR;
-    d.streams[live].indexed = s.inflation_indexed != 0;
-    live_start_age[live] = s.start_at_age;
-    live_duration[live] = d.streams[live].duration;
-    ++live;
-  }
-  d.n_streams = live;
+  *st = ctx->own_stream;
   return MCR_OK;
 }
 
@@ -178,18 +118,8 @@ int check_months(mcr_ctx* ctx, int32_t wm) {
   return MCR_OK;
 }
 
-// per live stream: [first paying retirement month, end) — simulation.py:602-621,653-656
 void fill_windows(const mcr_ctx* ctx, int32_t wm, int32_t* out) {
-  for (int k = 0; k < MCR_MAX_STREAMS; ++k) {
-    int32_t first = 0, end = 0;
-    if (k < ctx->dev.n_streams) {
-      first = start_month_index(ctx->params.current_age, wm, ctx->live_start_age[k]);
-      const int64_t e = ctx->live_duration[k] < 0 ? 2147483647ll : (int64_t)first + ctx->live_duration[k];
-      end = e > 2147483647ll ? 2147483647 : (int32_t)e;
-    }
-    out[2 * k] = first;
-    out[2 * k + 1] = end;
-  }
+  stream_windows(ctx->dev, ctx->params.current_age, ctx->live_start_age, ctx->live_duration, wm, out);
 }
 
 }  // namespace
@@ -238,9 +168,7 @@ int mcr_create(const mcr_params* params, uint64_t main_seed, int device, mcr_ctx
   std::memcpy(ctx->live_start_age, live_age, sizeof(live_age));
   std::memcpy(ctx->live_duration, live_dur, sizeof(live_dur));
   ctx->main_seed = main_seed;
-  const uint64_t key = splitmix64(splitmix64(main_seed) ^ 0x6D63725F62323030ull /* "mcr_b200" */);
-  ctx->k0 = (uint32_t)key;
-  ctx->k1 = (uint32_t)(key >> 32);
+  philox_key_from_seed(main_seed, ctx->k0, ctx->k1);
   philox_expand_keys(ctx->k0, ctx->k1, ctx->keys);
   *out_ctx = ctx;
   return MCR_OK;
@@ -250,11 +178,23 @@ int mcr_destroy(mcr_ctx* ctx) {
   if (!ctx) return MCR_OK;
   {
     DeviceGuard g(ctx->device);
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto& kv : ctx->scratch)
+      if (kv.second.p) {
+        cudaStreamSynchronize(kv.first);
+        cudaFree(kv.second.p);
+      }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   }
   delete ctx;
   return MCR_OK;
 }
+
+double mcr_small_returns_bound(const mcr_ctx* ctx) {
+  if (!ctx) return 0.0;
+  return ctx->dev.exp_small == 2 ? 0.05 : (ctx->dev.exp_small == 1 ? 0.1 : 0.0);
+}
+
+int32_t mcr_last_variant(const mcr_ctx* ctx) { return ctx ? ctx->last_variant : -1; }
 
 int64_t mcr_launch_count(const mcr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -277,7 +217,11 @@ int mcr_simulate(mcr_ctx* ctx, int seed_stream, int32_t working_months, int64_t 
   A.first_path = first_path; A.n_paths = n_paths;
   fill_windows(ctx, working_months, A.window);
   A.out = *out;
-  MCR_CUDA(ctx, pick(flags).timeline(ctx->dev, A, false, (cudaStream_t)stream));
+  // fast build: the variant for the bound on the monthly log-returns proven at mcr_create
+  const bool fast = !(flags & MCR_FLAG_STRICT);
+  const int cfg = pick_cfg_index(ctx->dev, fast, fast ? ctx->dev.exp_small : 0);
+  ctx->last_variant = cfg;
+  MCR_CUDA(ctx, pick(flags).timeline(ctx->dev, A, false, cfg, (cudaStream_t)stream));
   ctx->launches += 1;
   return MCR_OK;
 }
@@ -304,7 +248,11 @@ int mcr_replay(mcr_ctx* ctx, const double* shocks_dev, int64_t shocks_ld, int32_
   A.shocks_ld = shocks_ld;
   A.n_months = n_months;
   A.out = *out;
-  MCR_CUDA(ctx, pick(flags).timeline(ctx->dev, A, true, (cudaStream_t)stream));
+  // supplied draws: bounded only if the caller vouches for it (MCR_FLAG_SMALL_RETURNS)
+  const bool fast = !(flags & MCR_FLAG_STRICT);
+  const int cfg = pick_cfg_index(ctx->dev, fast, (fast && (flags & MCR_FLAG_SMALL_RETURNS)) ? ctx->dev.exp_small : 0);
+  ctx->last_variant = cfg;
+  MCR_CUDA(ctx, pick(flags).timeline(ctx->dev, A, true, cfg, (cudaStream_t)stream));
   ctx->launches += 1;
   return MCR_OK;
 }
@@ -323,8 +271,11 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
   // scratch layout: shocks[n*3] | traj[T] | real[T] | wr[R] | 5 doubles | ruin i32 | success u8
   const size_t n_sh = (size_t)n_months * 3;
   const size_t doubles = n_sh + 2 * (size_t)T + (size_t)R + 5;
-  if (int rc = ensure_scratch(ctx, doubles * 8 + 16)) return rc;
-  double* base = (double*)ctx->scratch;
+  cudaStream_t st;
+  if (int rc = own_stream(ctx, &st)) return rc;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, doubles * 8 + 16, &scratch)) return rc;
+  double* base = (double*)scratch;
   double* d_sh = base;
   double* d_traj = d_sh + n_sh;
   double* d_real = d_traj + T;
@@ -332,7 +283,6 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
   double* d_sc = d_wr + R;
   int32_t* d_ruin = (int32_t*)(d_sc + 5);
   uint8_t* d_succ = (uint8_t*)(d_ruin + 1);
-  cudaStream_t st = 0;
   MCR_CUDA(ctx, cudaMemcpyAsync(d_sh, shocks_host, n_sh * 8, cudaMemcpyHostToDevice, st));
   TimelineArgs A;
   std::memset(&A, 0, sizeof(A));
@@ -353,7 +303,7 @@ int mcr_single_path(mcr_ctx* ctx, int32_t working_months, const double* shocks_h
   A.out.real_trajectory = d_real;
   A.out.wr_trajectory = d_wr;
   A.out.series_ld = 1;
-  MCR_CUDA(ctx, strict_launchers().timeline(ctx->dev, A, true, st));
+  MCR_CUDA(ctx, strict_launchers().timeline(ctx->dev, A, true, pick_cfg_index(ctx->dev, false, 0), st));
   ctx->launches += 1;
   std::vector<double> h(2 * (size_t)T + R + 5 + 2);
   MCR_CUDA(ctx, cudaMemcpyAsync(h.data(), d_traj, (2 * (size_t)T + R + 5) * 8 + 8, cudaMemcpyDeviceToHost, st));
@@ -384,10 +334,14 @@ static int run_helper(mcr_ctx* ctx, int which, double a, double b, double c, dou
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
-  if (int rc = ensure_scratch(ctx, 64)) return rc;
-  MCR_CUDA(ctx, strict_launchers().helper(ctx->dev, which, a, b, c, d, use_tax, rate, e, (double*)ctx->scratch, 0));
+  cudaStream_t st;
+  if (int rc = own_stream(ctx, &st)) return rc;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, 64, &scratch)) return rc;
+  MCR_CUDA(ctx, strict_launchers().helper(ctx->dev, which, a, b, c, d, use_tax, rate, e, (double*)scratch, st));
   ctx->launches += 1;
-  MCR_CUDA(ctx, cudaMemcpy(out_host, ctx->scratch, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost));
+  MCR_CUDA(ctx, cudaMemcpyAsync(out_host, scratch, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost, st));
+  MCR_CUDA(ctx, cudaStreamSynchronize(st));
   return MCR_OK;
 }
 
@@ -454,21 +408,25 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
     h_slot[k] = c;
     fill_windows(ctx, candidates_host[c], h_sm + k * 2 * MCR_MAX_STREAMS);
   }
-  if (int rc = ensure_scratch(ctx, h.size() * 4)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, h.size() * 4, &scratch)) return rc;
   // pageable source: the copy is staged before the call returns, so `h` may go out of scope
-  MCR_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+  MCR_CUDA(ctx, cudaMemcpyAsync(scratch, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
   SearchArgs A;
   std::memset(&A, 0, sizeof(A));
   A.keys = ctx->keys; A.seed_stream = (uint32_t)seed_stream;
   A.n_candidates = n_candidates;
   A.first_path = first_path; A.n_paths = n_paths;
-  A.wm = (const int32_t*)ctx->scratch;
+  A.wm = (const int32_t*)scratch;
   A.slot = A.wm + per;
   A.window = A.slot + per;
   A.success_counts = success_counts_dev;
   A.executed_months = executed_months_dev;
-  MCR_CUDA(ctx, pick(flags).search(ctx->dev, A, st));
+  const bool fast = !(flags & MCR_FLAG_STRICT);
+  const int cfg = pick_cfg_index(ctx->dev, fast, fast ? ctx->dev.exp_small : 0);
+  ctx->last_variant = cfg;
+  MCR_CUDA(ctx, pick(flags).search(ctx->dev, A, cfg, st));
   ctx->launches += 1;
   return MCR_OK;
 }
@@ -509,10 +467,11 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
   const size_t hb = quantile_hist_bytes(n_rows);
-  if (int rc = ensure_scratch(ctx, hb + quantile_state_bytes(n_rows))) return rc;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, (cudaStream_t)stream, hb + quantile_state_bytes(n_rows), &scratch)) return rc;
   int n_launches = 0;
   MCR_CUDA(ctx, launch_quantiles_rows(n_rows, d.data(), out_dev, MCR_MAX_QUANTILES, counts_dev,
-                                      (char*)ctx->scratch + hb, ctx->scratch, (cudaStream_t)stream, &n_launches));
+                                      (char*)scratch + hb, scratch, (cudaStream_t)stream, &n_launches));
   ctx->launches += n_launches;
   return MCR_OK;
 }
@@ -536,9 +495,10 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
   const size_t hb = quantile_hist_bytes(rows);
-  if (int rc = ensure_scratch(ctx, hb + quantile_state_bytes(rows))) return rc;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, (cudaStream_t)stream, hb + quantile_state_bytes(rows), &scratch)) return rc;
   int n_launches = 0;
-  MCR_CUDA(ctx, launch_quantiles_rows(rows, d.data(), out_dev, n_q, counts_dev, (char*)ctx->scratch + hb, ctx->scratch,
+  MCR_CUDA(ctx, launch_quantiles_rows(rows, d.data(), out_dev, n_q, counts_dev, (char*)scratch + hb, scratch,
                                       (cudaStream_t)stream, &n_launches));
   ctx->launches += n_launches;
   return MCR_OK;
@@ -624,6 +584,17 @@ int mcr_first_year_rates(mcr_ctx* ctx, const double* start_dev, const double* fi
   return MCR_OK;
 }
 
+int mcr_years_to_ruin(mcr_ctx* ctx, const int32_t* ruin_month_dev, int64_t n, double* years_dev, void* stream) {
+  if (!ctx || !ruin_month_dev || !years_dev) return fail(ctx, MCR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n < 0) return fail(ctx, MCR_EINVAL, "negative n");
+  DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
+  MCR_CUDA(ctx, launch_years_to_ruin(ruin_month_dev, n, years_dev, (cudaStream_t)stream));
+  ctx->launches += n > 0;
+  return MCR_OK;
+}
+
 int mcr_minmax(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, int64_t n, double divisor,
                double* minmax_dev, void* stream) {
   if (!ctx || !values_dev || !minmax_dev) return fail(ctx, MCR_EINVAL, "null argument");
@@ -631,8 +602,11 @@ int mcr_minmax(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_dev, 
   if (n < 0 || !(divisor > 0)) return fail(ctx, MCR_EINVAL, "bad n / divisor");
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
-  if (int rc = ensure_scratch(ctx, 64)) return rc;
-  MCR_CUDA(ctx, launch_minmax(values_dev, mask_dev, n, divisor, (unsigned long long*)ctx->scratch, minmax_dev,
+  // the key pair lives behind the caller's output (minmax_dev[2..3] would be caller memory we do
+  // not own): a per-stream scratch slot, consumed by k_minmax_finish before the call's last launch
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, (cudaStream_t)stream, 64, &scratch)) return rc;
+  MCR_CUDA(ctx, launch_minmax(values_dev, mask_dev, n, divisor, (unsigned long long*)scratch, minmax_dev,
                               (cudaStream_t)stream));
   ctx->launches += 2 + (n > 0);
   return MCR_OK;
@@ -662,10 +636,11 @@ int mcr_gather_columns(mcr_ctx* ctx, const double* series_dev, int64_t ld, int32
   if (n_cols == 0 || rows == 0) return MCR_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
-  if (int rc = ensure_scratch(ctx, (size_t)n_cols * 8)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  MCR_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, cols_host, (size_t)n_cols * 8, cudaMemcpyHostToDevice, st));
-  MCR_CUDA(ctx, launch_gather(series_dev, ld, rows, (const int64_t*)ctx->scratch, n_cols, out_dev, st));
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, (size_t)n_cols * 8, &scratch)) return rc;
+  MCR_CUDA(ctx, cudaMemcpyAsync(scratch, cols_host, (size_t)n_cols * 8, cudaMemcpyHostToDevice, st));
+  MCR_CUDA(ctx, launch_gather(series_dev, ld, rows, (const int64_t*)scratch, n_cols, out_dev, st));
   ctx->launches += 1;
   return MCR_OK;
 }
@@ -675,16 +650,19 @@ int mcr_fp64_peak_slots_per_s(mcr_ctx* ctx, double* slots_per_s_host) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
-  if (int rc = ensure_scratch(ctx, 64)) return rc;
+  cudaStream_t st;
+  if (int rc = own_stream(ctx, &st)) return rc;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, 64, &scratch)) return rc;
   cudaEvent_t e0, e1;
   MCR_CUDA(ctx, cudaEventCreate(&e0));
   MCR_CUDA(ctx, cudaEventCreate(&e1));
   int threads = 0, per_thread = 0;
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {  // rep 0 is the warm-up
-    MCR_CUDA(ctx, cudaEventRecord(e0, 0));
-    MCR_CUDA(ctx, launch_fp64_peak(ctx->sm_count, 4096, (double*)ctx->scratch, 0, &threads, &per_thread));
-    MCR_CUDA(ctx, cudaEventRecord(e1, 0));
+    MCR_CUDA(ctx, cudaEventRecord(e0, st));
+    MCR_CUDA(ctx, launch_fp64_peak(ctx->sm_count, 4096, (double*)scratch, st, &threads, &per_thread));
+    MCR_CUDA(ctx, cudaEventRecord(e1, st));
     MCR_CUDA(ctx, cudaEventSynchronize(e1));
     ctx->launches += 1;
     float ms = 0.f;

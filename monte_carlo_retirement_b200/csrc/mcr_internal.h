@@ -36,8 +36,8 @@ struct SearchArgs {
 };
 
 struct Launchers {
-  cudaError_t (*timeline)(const DevParams&, const TimelineArgs&, bool replay, cudaStream_t);
-  cudaError_t (*search)(const DevParams&, const SearchArgs&, cudaStream_t);
+  cudaError_t (*timeline)(const DevParams&, const TimelineArgs&, bool replay, int cfg, cudaStream_t);  // cfg: pick_cfg_index()
+  cudaError_t (*search)(const DevParams&, const SearchArgs&, int cfg, cudaStream_t);
   cudaError_t (*draw)(const DevParams&, const PhiloxKeys& keys, uint32_t seed_stream, int64_t first_path,
                       int64_t n_paths, int32_t n_months, double* shocks, int64_t ld, cudaStream_t);
   cudaError_t (*helper)(const DevParams&, int which, double a, double b, double c, double d, int use_tax,

@@ -2,6 +2,7 @@
 // mcr_kernels_strict.cu (MCR_FAST=0, -fmad=false) and mcr_kernels_fast.cu (MCR_FAST=1), which
 // export the same launcher table under two names (see mcr_internal.h).
 #pragma once
+#include "mcr_derive.h"
 #include "mcr_internal.h"
 #include "mcr_path.cuh"
 #include "mcr_rng.cuh"
@@ -155,16 +156,6 @@ __global__ void k_helper(const __grid_constant__ DevParams P, int which, double 
 }
 
 // ---- launchers ---------------------------------------------------------------------------
-// which compile-time specialisation matches this scenario (0 generic, 1 both taxed, 2 no tax;
-// +2 when the short exp polynomial is provably enough — native draws of the fast build only)
-static int pick_cfg(const DevParams& P, bool native_draws) {
-  const int small = (MCR_FAST != 0 && native_draws && P.exp_small) ? 2 : 0;
-  // the both-taxed specialisation uses closed forms that need 1 - rate > eps
-  if (P.taxed1 && P.taxed2 && !P.annual_any && P.rate1 <= 0.999 && P.rate2 <= 0.999) return 1 + small;
-  if (!P.taxed1 && !P.taxed2 && !P.annual_any) return 2 + small;
-  return 0;
-}
-
 template <class C>
 static void launch_timeline_cfg(const DevParams& P, const TimelineArgs& A, bool replay, unsigned grid, size_t smem,
                                 cudaStream_t st) {
@@ -174,29 +165,34 @@ static void launch_timeline_cfg(const DevParams& P, const TimelineArgs& A, bool 
     k_timeline<MCR_FAST != 0, false, C><<<grid, kBlock, smem, st>>>(P, A);
 }
 
-static cudaError_t launch_timeline(const DevParams& P, const TimelineArgs& A, bool replay, cudaStream_t st) {
+// cfg: pick_cfg_index(P, fast, level of the bound on the monthly log-returns) — chosen by the API layer
+static cudaError_t launch_timeline(const DevParams& P, const TimelineArgs& A, bool replay, int cfg, cudaStream_t st) {
   const unsigned grid = (unsigned)((A.n_paths + kBlock - 1) / kBlock);
   const size_t smem = A.out.wr_obs_count ? sizeof(uint32_t) * (size_t)(P.R + 1) : 0;
-  switch (pick_cfg(P, !replay)) {
+  switch (cfg) {
     case 1: launch_timeline_cfg<CfgBothTaxed>(P, A, replay, grid, smem, st); break;
     case 2: launch_timeline_cfg<CfgNoTax>(P, A, replay, grid, smem, st); break;
 #if MCR_FAST
-    case 3: k_timeline<true, false, CfgBothTaxedSmall><<<grid, kBlock, smem, st>>>(P, A); break;
-    case 4: k_timeline<true, false, CfgNoTaxSmall><<<grid, kBlock, smem, st>>>(P, A); break;
+    case 3: launch_timeline_cfg<CfgBothTaxedSmall>(P, A, replay, grid, smem, st); break;
+    case 4: launch_timeline_cfg<CfgNoTaxSmall>(P, A, replay, grid, smem, st); break;
+    case 5: launch_timeline_cfg<CfgBothTaxedTight>(P, A, replay, grid, smem, st); break;
+    case 6: launch_timeline_cfg<CfgNoTaxTight>(P, A, replay, grid, smem, st); break;
 #endif
     default: launch_timeline_cfg<CfgGeneric>(P, A, replay, grid, smem, st); break;
   }
   return cudaGetLastError();
 }
 
-static cudaError_t launch_search(const DevParams& P, const SearchArgs& A, cudaStream_t st) {
+static cudaError_t launch_search(const DevParams& P, const SearchArgs& A, int cfg, cudaStream_t st) {
   dim3 grid((unsigned)((A.n_paths + kBlock - 1) / kBlock), (unsigned)A.n_candidates);
-  switch (pick_cfg(P, true)) {
+  switch (cfg) {
     case 1: k_search<MCR_FAST != 0, CfgBothTaxed><<<grid, kBlock, 0, st>>>(P, A); break;
     case 2: k_search<MCR_FAST != 0, CfgNoTax><<<grid, kBlock, 0, st>>>(P, A); break;
 #if MCR_FAST
     case 3: k_search<true, CfgBothTaxedSmall><<<grid, kBlock, 0, st>>>(P, A); break;
     case 4: k_search<true, CfgNoTaxSmall><<<grid, kBlock, 0, st>>>(P, A); break;
+    case 5: k_search<true, CfgBothTaxedTight><<<grid, kBlock, 0, st>>>(P, A); break;
+    case 6: k_search<true, CfgNoTaxTight><<<grid, kBlock, 0, st>>>(P, A); break;
 #endif
     default: k_search<MCR_FAST != 0, CfgGeneric><<<grid, kBlock, 0, st>>>(P, A); break;
   }

@@ -11,10 +11,9 @@
 // == target, its sale pays no tax and its cost basis never reaches an output.
 #pragma once
 #include <cstdint>
-#include <cuda_runtime.h>
-#include <math_constants.h>
 
 #include "../../include/mcr.h"
+#include "mcr_portable.h"
 
 namespace mcr {
 
@@ -46,14 +45,40 @@ struct DevParams {
   int32_t annual_any;      // some asset can owe annual tax (needs the P&L accumulators)
   int32_t R;               // retirement_years
   int32_t algebra_ok;      // some realized-gains tax bites and every such rate is < 1: closed forms allowed
-  int32_t exp_small;       // |monthly log-return| < 0.1 guaranteed for Philox normals (|z| <= 6.8)
+  int32_t exp_small;       // bound on |monthly log-return| proven for Philox normals (|z| <= 6.8): 2: < 0.05, 1: < 0.1, 0: none
   int32_t n_streams;       // streams with a positive amount, original order
+  int32_t lean_cfg_ok;     // allocation in [0.01, 0.99] and every biting realized-gains rate <= 0.9 (lean months)
+  double lean_cg;          // 0.5 * (1 - max biting rate) * exp(-0.2): W * lean_cg > E * level  =>  need < cap / 2
+  double lean_guard0;      // kLeanMinW * lean_cg (folded into the same comparison)
+  double lean_level_max;   // yearly check: E * level stays < 1e8 for the next 12 months
   DevStream streams[MCR_MAX_STREAMS];
 };
 
+// ---- lean months (fast build) -------------------------------------------------------------------
+// While a path is far from every threshold of the reference's helpers, a month is straight-line
+// arithmetic: no eps snap, no early-out, no clamp can be active. Sufficient conditions, all
+// checked ahead of the month (DevParams::lean_*, `bal` in run_timeline):
+//   * the portfolio is exactly on target after the last rebalance (b1 = a1*W, b2 = W - b1) and
+//     W > kLeanMinW dollars, allocation in [0.01, 0.99]  => every balance the month sees is > 0.1;
+//   * every monthly log-return is in (-0.1, 0.1) (Cfg::kExpSmall), every biting rate <= 0.9, and
+//     W * lean_cg > E * level  => need <= E * level < cap / 2: the full need is met (target ==
+//     need, the fraction withdrawn f < 1/2), no failure test can fire;
+//   * price level in (4e-3, lean_level_max), re-checked every retirement year.
+// Then (reference: simulation.py:692-796 for a retirement month, :519-553 for an accumulation
+// month) the month reduces to: growth; tax due on liquidation tx_i = max(0, b_i - cb_i) * rate_i;
+// cap = V - tx1 - tx2; f = need / cap; everything scales by q = 1 - f; and the rebalance, which
+// solves (b_s - x) = a_s * (V - tax(x)) exactly, leaves the portfolio ON TARGET with
+// W' = q * (V - fs * tx_s), fs = |drift| / (b_s - a_s * tx_s). Same formulas in exact
+// arithmetic; only the association of the products differs (<= 1e-15 relative per month).
+#ifndef MCR_COUNT_LEAN_MONTH
+#define MCR_COUNT_LEAN_MONTH()   // tests/host_model counts the months that took the lean step
+#endif
+constexpr double kLeanMinW = 16.0;
+constexpr double kLeanLevelMin = 4e-3;
+
 // income of one stream in retirement month r (simulation.py:650-677); `lock` holds the nominal
 // amount a non-indexed stream froze at its first payment (NaN-free sentinel: locked flag).
-__device__ __forceinline__ void stream_income(const DevStream& st, int first, int end, int r, double level0,
+MCR_DEV void stream_income(const DevStream& st, int first, int end, int r, double level0,
                                               double& lock, bool& is_locked, double& income) {
   if (r >= first && r < end) {
     double nominal;
@@ -80,79 +105,118 @@ struct PathOut {
 // picks a specialisation when the scenario matches one (-1 = read the flag at run time).
 template <int TAXED1, int TAXED2, int ANNUAL, int EXPSMALL = 0>
 struct Cfg {
-  // EXPSMALL: the host proved |mu/12| + sigma/sqrt(12) * z_max < 0.1 for all three factors (the
-  // Box-Muller normals of 32-bit uniforms are bounded by 6.77), so a short polynomial
-  // (Math::poly_exp_small) is accurate far below the noise of the MUFU normals and no range
-  // test is needed. Native-RNG launches only.
+  // EXPSMALL: |mu/12 + sigma/sqrt(12) * z| is bounded for all three factors — proven by the host
+  // for the Box-Muller normals of 32-bit uniforms (|z| <= 6.77), or guaranteed by the caller of a
+  // replay (MCR_FLAG_SMALL_RETURNS) — so a short Taylor polynomial of the unreduced argument needs
+  // no range test: level 2 (< 0.05) degree 6, level 1 (< 0.1) degree 8; truncation x^(d+1)/(d+1)!
+  // <= 3e-15 at the respective bound's typical 5-sigma draw, i.e. at rounding level.
+  static constexpr int kExpDegree = EXPSMALL == 2 ? 6 : 8;
   static constexpr bool kExpSmall = EXPSMALL != 0;
   // kAlgebra: both assets taxed on realized gains with rate < 1 (checked by the launcher): the
   // fast build may use the closed forms of the withdrawal pair and of the rebalance sale (see
   // withdraw_pair_closed / rebalance_main).
   static constexpr bool kAlgebra = TAXED1 == 1 && TAXED2 == 1 && ANNUAL == 0;
+  // kLean: the tax switches are compile-time, no annual tax, bounded monthly returns: the fast
+  // build may take the lean month steps (see "lean months" above)
+  static constexpr bool kLean = TAXED1 >= 0 && TAXED2 >= 0 && ANNUAL == 0 && EXPSMALL != 0;
+  static constexpr bool kAnyTaxed = TAXED1 != 0 || TAXED2 != 0;
   // generic configuration: the same closed forms behind a (warp-uniform) run-time test
-  static __device__ __forceinline__ bool algebra(const DevParams& P) {
+  static MCR_DEV bool algebra(const DevParams& P) {
     if constexpr (TAXED1 < 0) return P.algebra_ok != 0; else return kAlgebra;
   }
-  static __device__ __forceinline__ bool taxed1(const DevParams& P) {
+  static MCR_DEV bool taxed1(const DevParams& P) {
     if constexpr (TAXED1 < 0) return P.taxed1 != 0; else return TAXED1 != 0;
   }
-  static __device__ __forceinline__ bool taxed2(const DevParams& P) {
+  static MCR_DEV bool taxed2(const DevParams& P) {
     if constexpr (TAXED2 < 0) return P.taxed2 != 0; else return TAXED2 != 0;
   }
-  static __device__ __forceinline__ bool annual(const DevParams& P) {
+  static MCR_DEV bool annual(const DevParams& P) {
     if constexpr (ANNUAL < 0) return P.annual_any != 0; else return ANNUAL != 0;
   }
 };
 using CfgGeneric = Cfg<-1, -1, -1>;
 using CfgBothTaxed = Cfg<1, 1, 0>;   // both assets on the realized-gains system with a positive rate, no annual tax
 using CfgNoTax = Cfg<0, 0, 0>;       // no realized-gains tax bites and no annual tax
-using CfgBothTaxedSmall = Cfg<1, 1, 0, 1>;
+using CfgBothTaxedSmall = Cfg<1, 1, 0, 1>;   // |monthly log-return| < 0.1
 using CfgNoTaxSmall = Cfg<0, 0, 0, 1>;
+using CfgBothTaxedTight = Cfg<1, 1, 0, 2>;   // |monthly log-return| < 0.05
+using CfgNoTaxTight = Cfg<0, 0, 0, 2>;
 
 // CPython max(a, b) / min(a, b): first argument wins ties and NaN compares. Written as
 // setp + selp so the compiler cannot canonicalise them into fmax/fmin, whose NaN-correct SASS
 // expansion is 6 instructions instead of DSETP + 2 SEL.
-__device__ __forceinline__ double pmax(double a, double b) {
+MCR_DEV double pmax(double a, double b) {
+#ifdef __CUDA_ARCH__
   double d;
   asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(d) : "d"(a), "d"(b));
   return d;
+#else
+  return b > a ? b : a;
+#endif
 }
-__device__ __forceinline__ double pmin(double a, double b) {
+MCR_DEV double pmin(double a, double b) {
+#ifdef __CUDA_ARCH__
   double d;
   asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(d) : "d"(a), "d"(b));
   return d;
+#else
+  return b < a ? b : a;
+#endif
 }
 
 // (a <= c) || (|b| <= c) and (a < c) || (b < c) as two DSETPs + a predicate OR. Written in PTX
 // because the compiler otherwise rewrites the pair into fmin(a, b) < c, whose NaN-correct
 // expansion costs 6 instructions.
-__device__ __forceinline__ bool either_le_abs(double a, double b, double c) {
+MCR_DEV bool either_le_abs(double a, double b, double c) {
+#ifndef __CUDA_ARCH__
+  return a <= c || std::fabs(b) <= c;
+#else
   uint32_t r;
   asm("{\n\t.reg .pred p, q;\n\t.reg .f64 t;\n\tabs.f64 t, %2;\n\tsetp.le.f64 p, %1, %3;\n\t"
       "setp.le.f64 q, t, %3;\n\tor.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(r) : "d"(a), "d"(b), "d"(c));
   return r != 0;
+#endif
 }
-__device__ __forceinline__ bool either_le(double a, double b, double c) {
+MCR_DEV bool either_le(double a, double b, double c) {
+#ifndef __CUDA_ARCH__
+  return a <= c || b <= c;
+#else
   uint32_t r;
   asm("{\n\t.reg .pred p, q;\n\tsetp.le.f64 p, %1, %3;\n\tsetp.le.f64 q, %2, %3;\n\tor.pred p, p, q;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(r) : "d"(a), "d"(b), "d"(c));
   return r != 0;
+#endif
 }
-__device__ __forceinline__ bool either_lt(double a, double b, double c) {
+MCR_DEV bool either_lt(double a, double b, double c) {
+#ifndef __CUDA_ARCH__
+  return a < c || b < c;
+#else
   uint32_t r;
   asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %1, %3;\n\tsetp.lt.f64 q, %2, %3;\n\tor.pred p, p, q;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(r) : "d"(a), "d"(b), "d"(c));
   return r != 0;
+#endif
 }
 
 // exp(x) Taylor coefficients 1/13! .. 1/2! — constant-bank operands of the DFMAs (no UMOV pairs)
-static __constant__ double kExpC[12] = {
-    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
-    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
-    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
+#define MCR_EXP_COEFFS                                                                             \
+  {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,    \
+   2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,    \
+   8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5}
+#if defined(__CUDACC__)
+static __constant__ double kExpC[12] = MCR_EXP_COEFFS;
+#endif
+static constexpr double kExpCHost[12] = MCR_EXP_COEFFS;  // tests/host_model only
+MCR_DEV double expc(int i) {
+#ifdef __CUDA_ARCH__
+  return kExpC[i];
+#else
+  return kExpCHost[i];
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // math policy
@@ -160,10 +224,9 @@ static __constant__ double kExpC[12] = {
 template <bool FAST>
 struct Math {
   // reciprocal to ~1 ulp: MUFU.RCP64H seed + the 5-DFMA refinement (fast build only)
-  static __device__ __forceinline__ double rcp(double b) {
+  static MCR_DEV double rcp(double b) {
     if constexpr (FAST) {
-      double x0;
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(b));
+      const double x0 = rcp_seed(b);
       double e = fma(-b, x0, 1.0);
       double e2 = fma(e, e, e);
       double x1 = fma(x0, e2, x0);
@@ -173,47 +236,55 @@ struct Math {
       return 1.0 / b;
     }
   }
+  // lean months: seed (relative error e ~ 2^-20) + one cubic step, x0 * (1 + e + e^2): relative
+  // error e^3 ~ 1e-18 plus two roundings (<= ~2 ulp). The two extra DFMAs of rcp() only buy the
+  // last ulp, which the 1e-9 contract of this build does not need.
+  static MCR_DEV double rcp3(double b) {
+    const double x0 = rcp_seed(b);
+    const double e = fma(-b, x0, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(x0, e2, x0);
+  }
   // a / b: IEEE in the strict build; a * rcp(b) (<= 2 ulp, no slow-path branch) in the fast one
-  static __device__ __forceinline__ double div(double a, double b) {
+  static MCR_DEV double div(double a, double b) {
     if constexpr (FAST) return a * rcp(b);
     else return a / b;
   }
-  static __device__ __forceinline__ double poly_exp(double x) {
-    double p = kExpC[0];
+  static MCR_DEV double poly_exp(double x) {
+    double p = expc(0);
 #pragma unroll
-    for (int i = 1; i < 12; ++i) p = fma(p, x, kExpC[i]);
+    for (int i = 1; i < 12; ++i) p = fma(p, x, expc(i));
     p = fma(p, x, 1.0);
     return fma(p, x, 1.0);
   }
   // the three monthly gross factors exp(mu/12 + sigma/sqrt(12)*z) — simulation.py:468-474,522-530.
   // Fast build: ONE combined range test (integer compare on the high words), then three
   // interleaved Horner chains in a single basic block.
-  // Native-draw fast build only: degree 6, |x| < 0.1 (DevParams::exp_small). The truncation
-  // x^7/7! is < 2e-11 at the bound and ~1e-16 at a typical |x| of 0.02 — orders below the 3e-9
-  // the MUFU normals (5e-7 absolute on z) already put on every monthly factor of this build.
-  static __device__ __forceinline__ double poly_exp_small(double x) {
-    double p = kExpC[7];
+  // bounded argument (Cfg::kExpSmall): Taylor polynomial of degree DEG, no range test
+  template <int DEG>
+  static MCR_DEV double poly_exp_small(double x) {
+    double p = expc(13 - DEG);          // 1 / DEG!
 #pragma unroll
-    for (int i = 8; i < 12; ++i) p = fma(p, x, kExpC[i]);
+    for (int i = 14 - DEG; i < 12; ++i) p = fma(p, x, expc(i));
     p = fma(p, x, 1.0);
     return fma(p, x, 1.0);
   }
   template <class C>
-  static __device__ __forceinline__ void factors(const DevParams& P, double ze, double zi, double zp, double& G1,
+  static MCR_DEV void factors(const DevParams& P, double ze, double zi, double zp, double& G1,
                                                  double& GI, double& GP) {
     const double x1 = P.mu1 + P.sg1 * ze;  // strict: two roundings (no FMA); fast: one DFMA
     const double xi = P.muI + P.sgI * zi;
     const double xp = P.muP + P.sgP * zp;
     if constexpr (FAST && C::kExpSmall) {
-      G1 = poly_exp_small(x1);
-      GI = poly_exp_small(xi);
-      GP = poly_exp_small(xp);
+      G1 = poly_exp_small<C::kExpDegree>(x1);
+      GI = poly_exp_small<C::kExpDegree>(xi);
+      GP = poly_exp_small<C::kExpDegree>(xp);
       return;
     }
     if constexpr (FAST) {
-      const int h1 = __double2hiint(x1) & 0x7fffffff, hi = __double2hiint(xi) & 0x7fffffff,
-                hp = __double2hiint(xp) & 0x7fffffff;
-      if (__builtin_expect(max(h1, max(hi, hp)) < 0x3FD5C28F, 1)) {  // all |x| < 0.34
+      const int h1 = hi_word(x1) & 0x7fffffff, hi = hi_word(xi) & 0x7fffffff, hp = hi_word(xp) & 0x7fffffff;
+      const int hmax = h1 > hi ? (h1 > hp ? h1 : hp) : (hi > hp ? hi : hp);
+      if (__builtin_expect(hmax < 0x3FD5C28F, 1)) {  // all |x| < 0.34
         G1 = poly_exp(x1);
         GI = poly_exp(xi);
         GP = poly_exp(xp);
@@ -225,7 +296,7 @@ struct Math {
     GP = exp(xp);
   }
   // monthly gross factor exp(mu + sg * z) — simulation.py:468-474
-  static __device__ __forceinline__ double gross(double mu, double sg, double z) {
+  static MCR_DEV double gross(double mu, double sg, double z) {
     const double x = mu + sg * z;  // strict: two roundings (no FMA); fast: one DFMA
     if constexpr (FAST) {
       // |x| is a monthly log-return, far inside [-0.5 ln2, 0.5 ln2] for any sane scenario: a
@@ -233,9 +304,9 @@ struct Math {
       // |x| = 0.34, 13 DFMA instead of the library's 17 FP64 ops + range reduction), with the
       // general routine as the (warp-rare) fallback.
       if (__builtin_expect(fabs(x) < 0.34, 1)) {
-        double p = kExpC[0];
+        double p = expc(0);
 #pragma unroll
-        for (int i = 1; i < 12; ++i) p = fma(p, x, kExpC[i]);
+        for (int i = 1; i < 12; ++i) p = fma(p, x, expc(i));
         p = fma(p, x, 1.0);
         return fma(p, x, 1.0);
       }
@@ -258,7 +329,7 @@ struct Math {
 // ---------------------------------------------------------------------------------------------
 
 // _net_liquidation_value — simulation.py:256-272
-__device__ __forceinline__ double net_liq(double bal, double cb, bool taxed, double rate) {
+MCR_DEV double net_liq(double bal, double cb, bool taxed, double rate) {
   if (!taxed) return bal > kEps ? bal : 0.0;   // tax == 0.0; identity: max(0, bal - 0.0) with bal > eps
   const double gain = pmax(0.0, bal - cb);
   // identity: max(0, bal - gain*rate): gain <= bal and rate <= 1, so the difference is >= +0.0
@@ -268,7 +339,7 @@ __device__ __forceinline__ double net_liq(double bal, double cb, bool taxed, dou
 // _calculate_withdrawal_and_update — simulation.py:201-254
 // main path (the early-out of :218-219 is tested by the callers)
 template <bool FAST, bool FULL>
-__device__ __forceinline__ void withdraw_main(double& bal, double& cb, double target, bool taxed, double rate,
+MCR_DEV void withdraw_main(double& bal, double& cb, double target, bool taxed, double rate,
                                               double& gross, double& net) {
   if (!taxed && !FULL) {
     // effective tax fraction 0 -> net_fraction == 1.0, target / 1.0 == target, tax_paid == 0.
@@ -305,10 +376,10 @@ __device__ __forceinline__ void withdraw_main(double& bal, double& cb, double ta
   cb = ncb;
 }
 
-__device__ __forceinline__ bool withdraw_skips(double bal, double target) { return bal <= kEps || target <= 0; }
+MCR_DEV bool withdraw_skips(double bal, double target) { return bal <= kEps || target <= 0; }
 
 template <bool FAST, bool FULL>
-__device__ __forceinline__ void withdraw(double& bal, double& cb, double target, bool taxed, double rate,
+MCR_DEV void withdraw(double& bal, double& cb, double target, bool taxed, double rate,
                                          double& gross, double& net) {
   if (__builtin_expect(withdraw_skips(bal, target), 0)) {  // :218-219
     bal = pmax(0.0, bal);
@@ -323,7 +394,7 @@ __device__ __forceinline__ void withdraw(double& bal, double& cb, double target,
 // Both monthly withdrawals with ONE combined early-out test, so the two dependent chains sit in
 // one basic block and interleave (simulation.py:757-777).
 template <bool FAST, class C>
-__device__ __forceinline__ void withdraw_pair(const DevParams& P, double& b1, double& cb1, double t1, double& b2,
+MCR_DEV void withdraw_pair(const DevParams& P, double& b1, double& cb1, double t1, double& b2,
                                               double& cb2, double t2, double& gw1, double& nw1, double& gw2,
                                               double& nw2) {
   if (__builtin_expect(!(withdraw_skips(b1, t1) || withdraw_skips(b2, t2)), 1)) {
@@ -339,14 +410,14 @@ __device__ __forceinline__ void withdraw_pair(const DevParams& P, double& b1, do
 // folded into one straight-line body by selecting the roles (the direction differs per lane,
 // the flags do not), so a warp never executes both.
 // :290-296 — nothing to do when the portfolio is empty or already on target
-__device__ __forceinline__ bool rebalance_skips(const DevParams& P, double b1, double b2) {
+MCR_DEV bool rebalance_skips(const DevParams& P, double b1, double b2) {
   const double total = b1 + b2;
   const double drift1 = b1 - total * P.a1;
   return either_le_abs(total, drift1, kEps);
 }
 
 template <bool FAST, bool FULL, class C = CfgGeneric>
-__device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
+MCR_DEV void rebalance_main(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
   const double total = b1 + b2;
   const double drift1 = b1 - total * P.a1;                // :293-294
   const bool sell1 = drift1 > 0;
@@ -422,14 +493,14 @@ __device__ __forceinline__ void rebalance_main(const DevParams& P, double& b1, d
 }
 
 template <bool FAST, bool FULL, class C = CfgGeneric>
-__device__ __forceinline__ void rebalance(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
+MCR_DEV void rebalance(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2) {
   if (__builtin_expect(rebalance_skips(P, b1, b2), 0)) return;
   rebalance_main<FAST, FULL, C>(P, b1, cb1, b2, cb2);
 }
 
 // _apply_annual_gain_taxes — simulation.py:361-450. Returns tax_failed.
 template <bool FAST, bool FULL, class C = CfgGeneric>
-__device__ __forceinline__ bool annual_tax(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2,
+MCR_DEV bool annual_tax(const DevParams& P, double& b1, double& cb1, double& b2, double& cb2,
                                         double g1, double g2) {
   bool failed = false;
   if (C::annual(P)) {
@@ -461,8 +532,8 @@ __device__ __forceinline__ bool annual_tax(const DevParams& P, double& b1, doubl
 // ---------------------------------------------------------------------------------------------
 struct NullSink {
   static constexpr bool kActive = false;
-  __device__ __forceinline__ void point(int, double, double) {}
-  __device__ __forceinline__ void wr(int, double) {}
+  MCR_DEV void point(int, double, double) {}
+  MCR_DEV void wr(int, double) {}
 };
 
 // time-major [t][ld]: a warp's 32 paths store 256 contiguous bytes per point
@@ -472,14 +543,122 @@ struct SeriesSink {
   double* real;  // may be NULL
   double* wrp;   // may be NULL
   int64_t ld;
-  __device__ __forceinline__ void point(int t, double nominal, double price) {
-    if (traj) __stcs(traj + (int64_t)t * ld, nominal);
-    if (real) __stcs(real + (int64_t)t * ld, price > kEps ? nominal / price : 0.0);  // :928-931
+  MCR_DEV void point(int t, double nominal, double price) {
+    if (traj) store_stream(traj + (int64_t)t * ld, nominal);
+    if (real) store_stream(real + (int64_t)t * ld, price > kEps ? nominal / price : 0.0);  // :928-931
   }
-  __device__ __forceinline__ void wr(int y, double v) {
-    if (wrp) __stcs(wrp + (int64_t)y * ld, v);
+  MCR_DEV void wr(int y, double v) {
+    if (wrp) store_stream(wrp + (int64_t)y * ld, v);
   }
 };
+
+
+// ---------------------------------------------------------------------------------------------
+// lean month steps (fast build only; see "lean months" next to DevParams)
+// ---------------------------------------------------------------------------------------------
+struct Factors {
+  double G1, GI, GP;
+};
+
+// The rebalance of a portfolio (nb1, nb2) with cost bases (c1, c2) that is guaranteed to trade
+// without clamps: returns the fraction-sold bookkeeping applied to the cost bases and the total
+// after the sale's tax, V - fs * tx_s (simulation.py:298-353 solved in closed form).
+template <class C>
+MCR_DEV double lean_rebalance(const DevParams& P, double nb1, double nb2, double V, double tx1, double tx2,
+                              double& c1, double& c2) {
+  if constexpr (!C::kAnyTaxed) {
+    return V;  // no tax on the sale: the total is unchanged, cost bases are dead state
+  } else {
+    const double d0 = fma(-P.a1, V, nb1);          // drift of asset 1 (:293-294); asset 2 drifts by -d0
+    const bool sell1 = d0 > 0.0;
+    const double bs = sell1 ? nb1 : nb2;
+    const double gs = sell1 ? tx1 : tx2;           // tax due if the WHOLE selling asset were liquidated
+    const double cbs = sell1 ? c1 : c2;
+    const double as = sell1 ? P.a1 : P.a2;
+    const double fs = fabs(d0) * Math<true>::rcp3(fma(-as, gs, bs));   // fraction of the asset sold
+    const double tax = fs * gs;
+    const double buy = fma(fs, bs, -tax);          // sale - tax: what reaches the other asset
+    const double br = fs * cbs;                    // basis removed from the selling asset
+    if (sell1) { c1 -= br; c2 += buy; } else { c1 += buy; c2 -= br; }
+    return V - tax;
+  }
+}
+
+// accumulation month — simulation.py:519-553 (k1, k2: this year's contribution split)
+template <class C>
+MCR_DEV void lean_accumulate(const DevParams& P, const Factors& cur, double k1, double k2, double& b1, double& cb1,
+                             double& b2, double& cb2, double& level, bool& bal) {
+  const double G2 = cur.GI * cur.GP;
+  const double nb1 = fma(b1, cur.G1, k1);
+  const double nb2 = fma(b2, G2, k2);
+  level *= cur.GI;
+  const double V = nb1 + nb2;
+  double c1 = cb1 + k1, c2 = cb2 + k2;
+  const double tx1 = C::taxed1(P) ? pmax(0.0, nb1 - c1) * P.rate1 : 0.0;
+  const double tx2 = C::taxed2(P) ? pmax(0.0, nb2 - c2) * P.rate2 : 0.0;
+  const double Wn = lean_rebalance<C>(P, nb1, nb2, V, tx1, tx2, c1, c2);
+  cb1 = c1;
+  cb2 = c2;
+  b1 = P.a1 * Wn;
+  b2 = Wn - b1;
+  bal = Wn > kLeanMinW;
+}
+
+// retirement month — simulation.py:644-796 (cnet = E - sum(indexed amount * (1 - tax)), fixed = sum of the locked
+// nominal non-indexed payments * (1 - tax): need = max(0, cnet * level - fixed))
+template <class C>
+MCR_DEV void lean_decumulate(const DevParams& P, const Factors& cur, double cnet, double fixed, double level_ret,
+                             double& b1, double& cb1, double& b2, double& cb2, double& level, double& yr_gross,
+                             double& yr_real, bool& bal) {
+  const double level0 = level;
+  const double need = pmax(0.0, fma(cnet, level0, -fixed));
+  const double G2 = cur.GI * cur.GP;
+  const double nb1 = b1 * cur.G1;
+  const double nb2 = b2 * G2;
+  const double lv = level0 * cur.GI;
+  const double V = nb1 + nb2;
+  double c1 = cb1, c2 = cb2;
+  const double tx1 = C::taxed1(P) ? pmax(0.0, nb1 - c1) * P.rate1 : 0.0;   // tax due on full liquidation
+  const double tx2 = C::taxed2(P) ? pmax(0.0, nb2 - c2) * P.rate2 : 0.0;
+  double gross, q;
+  if constexpr (C::kAnyTaxed) {
+    // both withdrawals at once (:750-777): net target split by w_i = cap_i / cap and grossed up by
+    // b_i / cap_i, i.e. ONE fraction f = need / cap of every balance, basis and latent tax is sold
+    const double cap = V - (tx1 + tx2);
+    const double f = need * Math<true>::rcp3(cap);
+    q = 1.0 - f;
+    gross = f * V;
+  } else {
+    gross = need;  // no tax: gross == net == need (< V / 2)
+    q = 1.0;       // unused
+  }
+  yr_gross += gross;
+  yr_real = fma(gross * level_ret, Math<true>::rcp3(level0), yr_real);      // :778-782
+  // The rebalance's fraction sold is invariant under the common scale q, so it is computed from
+  // the pre-withdrawal values (its reciprocal then runs beside the one above) and q applied once.
+  const double Wu = lean_rebalance<C>(P, nb1, nb2, V, tx1, tx2, c1, c2);
+  double Wn;
+  if constexpr (C::kAnyTaxed) {
+    cb1 = q * c1;
+    cb2 = q * c2;
+    Wn = q * Wu;
+  } else {
+    Wn = Wu - need;
+  }
+  b1 = P.a1 * Wn;
+  b2 = Wn - b1;
+  level = lv;
+  bal = fma(Wn, P.lean_cg, -P.lean_guard0) > P.E * lv;   // W > kLeanMinW and next month's need < cap / 2
+}
+
+// (re-)entry test after a general month / at a phase change: on target, big enough, in range
+MCR_DEV bool lean_ready(const DevParams& P, double b1, double b2, double level, bool retired) {
+  const double W = b1 + b2;
+  bool ok = P.lean_cfg_ok != 0 && W > kLeanMinW && fabs(fma(-P.a1, W, b1)) <= 1e-13 * W;
+  if (retired)
+    ok = ok && fma(W, P.lean_cg, -P.lean_guard0) > P.E * level && level > kLeanLevelMin && level < P.lean_level_max;
+  return ok;
+}
 
 // ---------------------------------------------------------------------------------------------
 // the timeline
@@ -489,12 +668,8 @@ struct SeriesSink {
 // pure scheduling change: inside month a's basic blocks the compiler now has independent INT
 // (Philox), FP32/MUFU (Box-Muller) and FP64 (three exp polynomials) work to interleave with
 // the long dependent chains of the withdrawals and the rebalance.
-struct Factors {
-  double G1, GI, GP;
-};
-
 template <bool FAST, class C, class Shock, class Sink>
-__device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
+MCR_DEV void run_timeline(const DevParams& P, const int wm,
                                              const int32_t* __restrict__ window, Shock& shock,
                                              Sink& sink, PathOut& o, int& years_observed) {
   const int R = P.R;
@@ -516,35 +691,61 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
     Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
   }
 
+  constexpr bool kLean = FAST && C::kLean;
+  // lean mode (per path): the portfolio is exactly on target and far from every threshold, so the
+  // month can take the straight-line step; re-evaluated after every month
+  [[maybe_unused]] bool bal = false;
+  if constexpr (kLean) bal = P.lean_cfg_ok != 0 && P.B0 > kLeanMinW;
+  double k1 = contrib * P.a1;                                        // :540-547
+  double k2 = contrib - k1;
+
   // ---- accumulation — :513-579
   int moy = 0;  // (m-1) % 12
   for (int m = 1; m <= wm; ++m) {
-    if (moy == 0 && m > 1 && P.growth_on) contrib *= P.growth1p;   // :514-517
+    if (moy == 0 && m > 1 && P.growth_on) {                          // :514-517
+      contrib *= P.growth1p;
+      k1 = contrib * P.a1;
+      k2 = contrib - k1;
+    }
     const Factors cur = nxt;
     double ze, zi, zp;
     shock.next(ze, zi, zp);                                        // draws of the FOLLOWING month
     ++executed;
-    const double G2 = cur.GI * cur.GP;                             // :532
-    if (C::annual(P)) {
-      g1 += b1 * (cur.G1 - 1.0);                                   // :534-535
-      g2 += b2 * (G2 - 1.0);
+    bool lean_month = false;
+    if constexpr (kLean) {
+      if (__builtin_expect(bal, 1)) {
+        lean_accumulate<C>(P, cur, k1, k2, b1, cb1, b2, cb2, level, bal);
+        MCR_COUNT_LEAN_MONTH();
+        Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+        lean_month = true;
+      }
     }
-    b1 *= cur.G1;
-    b2 *= G2;
-    level *= cur.GI;
-    const double k1 = contrib * P.a1;                              // :540-547
-    const double k2 = contrib - k1;
-    b1 += k1; cb1 += k1;
-    b2 += k2; cb2 += k2;
-    if (__builtin_expect(!rebalance_skips(P, b1, b2), 1)) {        // :549-553
-      rebalance_main<FAST, false, C>(P, b1, cb1, b2, cb2);
-      Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
-    } else {
-      Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+    if (!lean_month) {
+      const double G2 = cur.GI * cur.GP;                             // :532
+      if (C::annual(P)) {
+        g1 += b1 * (cur.G1 - 1.0);                                   // :534-535
+        g2 += b2 * (G2 - 1.0);
+      }
+      b1 *= cur.G1;
+      b2 *= G2;
+      level *= cur.GI;
+      b1 += k1; cb1 += k1;
+      b2 += k2; cb2 += k2;
+      if (__builtin_expect(!rebalance_skips(P, b1, b2), 1)) {        // :549-553
+        rebalance_main<FAST, false, C>(P, b1, cb1, b2, cb2);
+        Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+      } else {
+        Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+      }
+      if constexpr (kLean) bal = lean_ready(P, b1, b2, level, false);
     }
     if (++moy == kMPY) {                                           // m % 12 == 0 — :557-579
       moy = 0;
-      if (annual_tax<FAST, false, C>(P, b1, cb1, b2, cb2, g1, g2)) pre_fail = true;
+      // lean mode: no annual tax and the portfolio is on target, so the trailing rebalance of the
+      // (empty) annual-tax event early-outs in the reference (:432-442 with |drift| <= eps)
+      if (!(kLean && lean_month)) {
+        if (annual_tax<FAST, false, C>(P, b1, cb1, b2, cb2, g1, g2)) pre_fail = true;
+      }
       sink.point(t++, b1 + b2, level);
       g1 = 0.0; g2 = 0.0;
     }
@@ -561,7 +762,9 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
   uint32_t lockn_mask = 0;
   const int ns = P.n_streams;
   double idx_coeff = 0.0, fixed_income = 0.0;  // fast build: cached stream sums
+  [[maybe_unused]] double cnet = P.E;          // lean months: E - idx_coeff
   int next_event = 0;                          // next retirement month at which they change
+  if constexpr (kLean) bal = !pre_fail && lean_ready(P, b1, b2, level, true);
   double fy_gross = 0.0, fy_real = 0.0;
   bool ok = !pre_fail;                                             // :627-629
   int ruin = pre_fail ? 0 : -1;
@@ -571,12 +774,14 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
 
   // ---- decumulation — :632-868
   for (; y < R && !pre_fail; ++y) {
-    double yr_g1 = 0.0, yr_g2 = 0.0, yr_real = 0.0;
+    double yr_g1 = 0.0, yr_g2 = 0.0, yr_real = 0.0;   // fast build: yr_g1 carries both assets' gross
     bool failed = false;
     int r = y * kMPY;
+    if constexpr (kLean) {  // price level range of the lean months, valid for the next 12 of them
+      if (!(level > kLeanLevelMin && level < P.lean_level_max)) bal = false;
+    }
     for (int j = 0; j < kMPY; ++j, ++r) {
       const double level0 = level;                                 // :644-647
-      const double need_nominal = P.E * level0;
       double income = 0.0;                                         // :649-677
       if constexpr (FAST) {
         // The set of paying streams changes only at window boundaries (warp-uniform months):
@@ -600,6 +805,22 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
             }
           }
           next_event = nxt_ev;
+          cnet = P.E - idx_coeff;
+        }
+        if constexpr (kLean) {
+          if (__builtin_expect(bal, 1)) {
+            const Factors cur = nxt;
+            double ze, zi, zp;
+            shock.next(ze, zi, zp);                                // draws of the FOLLOWING month
+            ++executed;
+            lean_decumulate<C>(P, cur, cnet, fixed_income, level_ret, b1, cb1, b2, cb2, level, yr_g1, yr_real, bal);
+            MCR_COUNT_LEAN_MONTH();
+            Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
+            // the month cannot fail, and the (empty) annual-tax event at a tax-year end reduces to
+            // a rebalance that early-outs on an on-target portfolio (:798-822, :432-442)
+            if (++tax_moy == kMPY) tax_moy = 0;
+            continue;
+          }
         }
         income = idx_coeff * level0 + fixed_income;
       } else {
@@ -613,6 +834,7 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
           if (lk && !was) { lockn[k] = lv; lockn_mask |= 1u << k; }
         }
       }
+      const double need_nominal = P.E * level0;
       const double need = pmax(0.0, need_nominal - income);        // :679-682
       const bool wants = need > kEps;
       if (__builtin_expect(b1 + b2 <= kEps && wants, 0)) { failed = true; break; }  // :684-690
@@ -677,8 +899,12 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
         const double w2 = 1.0 - w1;
         withdraw_pair<FAST, C>(P, b1, cb1, target * w1, b2, cb2, target * w2, gw1, nw1, gw2, nw2);  // :757-777
       }
-      yr_g1 += gw1;
-      yr_g2 += gw2;
+      if constexpr (FAST) {
+        yr_g1 += gw1 + gw2;
+      } else {
+        yr_g1 += gw1;
+        yr_g2 += gw2;
+      }
       yr_real += Math<FAST>::div((gw1 + gw2) * level_ret, pmax(level0, kEps));   // :778-782
       if (wants && either_lt(target, nw1 + nw2, need_lo)) failed = true;   // :743-748 and :784-790
       if (__builtin_expect(!rebalance_skips(P, b1, b2), 1)) {      // :792-796
@@ -694,13 +920,14 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
         if (tf) failed = true;
       }
       if (__builtin_expect(failed, 0)) { ruin = r + 1; break; }    // :824-828
+      if constexpr (kLean) bal = lean_ready(P, b1, b2, level, true);
     }
     const double yr_gross = yr_g1 + yr_g2;
     if (failed) {                                                  // :842-857
       ok = false;
       if (ruin < 0) ruin = r + 1;
       sink.point(t++, pmax(0.0, b1 + b2), level);
-      sink.wr(y, CUDART_NAN);
+      sink.wr(y, nan_value());
       if (y == 0) { fy_gross = yr_gross; fy_real = yr_real; }
       ++y;
       break;
@@ -721,7 +948,7 @@ __device__ __forceinline__ void run_timeline(const DevParams& P, const int wm,
   if (Sink::kActive) {
     const int T = 1 + (wm + kMPY - 1) / kMPY + R;
     for (; t < T; ++t) sink.point(t, 0.0, 1.0);
-    for (; y < R; ++y) sink.wr(y, CUDART_NAN);
+    for (; y < R; ++y) sink.wr(y, nan_value());
   }
 
   o.start_balance = S0;

@@ -832,6 +832,15 @@ __global__ void k_rates(const double* __restrict__ start, const double* __restri
   rates[i] = s > MCR_SMALL_EPSILON ? __dmul_rn(__ddiv_rn(fy_real[i], s), 100.0) : CUDART_NAN;
 }
 
+// YearsToRuin = ruin_month / 12 (IEEE division, as CPython's (r + 1) / 12 at simulation.py:825-828),
+// NaN for paths that never failed
+__global__ void k_years_to_ruin(const int32_t* __restrict__ ruin, int64_t n, double* __restrict__ years) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t m = ruin[i];
+  years[i] = m < 0 ? CUDART_NAN : __ddiv_rn((double)m, (double)MCR_MONTHS_PER_YEAR);
+}
+
 // ---- cohort min / max -----------------------------------------------------------------------
 __device__ __forceinline__ void atomic_min_key(unsigned long long* p, unsigned long long k) { atomicMin(p, k); }
 __device__ __forceinline__ void atomic_max_key(unsigned long long* p, unsigned long long k) { atomicMax(p, k); }
@@ -1081,6 +1090,12 @@ cudaError_t launch_sel_tail_pooled(int rows, void* state, long long* xbuf, int w
 cudaError_t launch_rates(const double* start, const double* fy_real, int64_t n, double* rates, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   k_rates<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(start, fy_real, n, rates);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_years_to_ruin(const int32_t* ruin, int64_t n, double* years, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_years_to_ruin<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ruin, n, years);
   return cudaGetLastError();
 }
 

@@ -46,6 +46,7 @@ cudaError_t launch_sel_finish(int rows, const void* state, double* out, int out_
 size_t quantile_state_bytes(int rows);
 size_t quantile_hist_bytes(int rows);
 cudaError_t launch_rates(const double* start, const double* fy_real, int64_t n, double* rates, cudaStream_t st);
+cudaError_t launch_years_to_ruin(const int32_t* ruin, int64_t n, double* years, cudaStream_t st);
 cudaError_t launch_minmax(const double* x, const uint8_t* mask, int64_t n, double divisor, unsigned long long* keys2,
                           double* minmax, cudaStream_t st);
 cudaError_t launch_histogram(const double* x, const uint8_t* mask, int64_t n, double divisor, int n_bins, int mode,

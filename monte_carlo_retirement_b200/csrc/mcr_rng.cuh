@@ -14,6 +14,8 @@
 #pragma once
 #include <cstdint>
 
+#include "mcr_portable.h"
+
 namespace mcr {
 
 // The key schedule (k + r*W per round) does not depend on the counter: the host expands it once
@@ -23,14 +25,14 @@ struct PhiloxKeys {
   uint32_t rk[20];  // rk[2r], rk[2r+1] = (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85)
 };
 
-__host__ __device__ inline void philox_expand_keys(uint32_t k0, uint32_t k1, PhiloxKeys& K) {
+MCR_DEV void philox_expand_keys(uint32_t k0, uint32_t k1, PhiloxKeys& K) {
   for (int r = 0; r < 10; ++r) {
     K.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
     K.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
   }
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+MCR_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKeys& K, uint32_t out[4]) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
@@ -51,37 +53,39 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // FAST: MUFU lg2 / sqrt / sin / cos (abs error ~5e-7 on a unit normal, invisible next to the
 // 1/sqrt(N) sampling error). !FAST: full-precision logf / sqrtf / sincospif.
 template <bool FAST>
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+MCR_DEV void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = fmaf(u32_to_float(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+#ifdef __CUDA_ARCH__
   if constexpr (FAST) {
     float lg, r, s, c;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
     const float t = lg * -1.3862943611198906f;  // -2 ln2 * log2(u1) = -2 ln(u1) >= 0
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
-    const float th = fmaf(__uint2float_rn(b), 1.4629180792671596e-09f, -3.1415926535897931f);
+    const float th = fmaf(u32_to_float(b), 1.4629180792671596e-09f, -3.1415926535897931f);
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
     n0 = r * c;
     n1 = r * s;
-  } else {
-    const float r = sqrtf(-2.0f * logf(u1));
-    const float turns = fmaf(__uint2float_rn(b), 4.6566128730773926e-10f, -1.0f);  // theta / pi in [-1, 1]
-    float s, c;
-    sincospif(turns, &s, &c);
-    n0 = r * c;
-    n1 = r * s;
+    return;
   }
+#endif
+  const float r = sqrtf(-2.0f * logf(u1));
+  const float turns = fmaf(u32_to_float(b), 4.6566128730773926e-10f, -1.0f);  // theta / pi in [-1, 1]
+  float s, c;
+  sincospi_f(turns, s, c);
+  n0 = r * c;
+  n1 = r * s;
 }
 
 struct ReplayShock {
   const double* p;  // shocks_dev + path
   int64_t ld;
   int32_t left;     // rows not yet consumed (the timeline prefetches one month ahead)
-  __device__ __forceinline__ void next(double& ze, double& zi, double& zp) {
+  MCR_DEV void next(double& ze, double& zi, double& zp) {
     if (left > 0) {
-      ze = __ldcs(p);
-      zi = __ldcs(p + ld);
-      zp = __ldcs(p + 2 * ld);
+      ze = load_stream(p);
+      zi = load_stream(p + ld);
+      zp = load_stream(p + 2 * ld);
       p += 3 * ld;
       --left;
     } else {
@@ -96,7 +100,7 @@ struct PhiloxShock {
   uint32_t p_lo, p_hi, month, strm;
   float rho_f, rho_c_f;
   double rho, rho_c;
-  __device__ __forceinline__ void next(double& ze, double& zi, double& zp) {
+  MCR_DEV void next(double& ze, double& zi, double& zp) {
     uint32_t r[4];
     philox4x32_10(p_lo, p_hi, month, strm, keys, r);
     ++month;

@@ -14,6 +14,7 @@ from typing import Any, Optional, Sequence
 
 MAX_STREAMS = 16
 FLAG_STRICT = 0x1
+FLAG_SMALL_RETURNS = 0x2
 STREAM_SEARCH = 0
 STREAM_FINAL = 1
 SEL_MEDIAN = 0x1
@@ -126,6 +127,8 @@ SIGNATURES = {
     "mcr_destroy": (C.c_int, [_VP]),
     "mcr_last_error": (C.c_char_p, [_VP]),
     "mcr_launch_count": (_I64, [_VP]),
+    "mcr_small_returns_bound": (_D, [_VP]),
+    "mcr_last_variant": (_I32, [_VP]),
     "mcr_stream_start_month": (_I32, [_D, _I32, _D]),
     "mcr_trajectory_len": (_I32, [_I32, _I32]),
     "mcr_simulate": (C.c_int, [_VP, C.c_int, _I32, _I64, _I64, _U32, C.POINTER(Outputs), _VP]),
@@ -146,6 +149,7 @@ SIGNATURES = {
     "mcr_quantiles_rows": (C.c_int, [_VP, C.POINTER(SelectRow), _I32, _VP, _VP, _VP]),
     "mcr_select_step": (C.c_int, [_VP, _I32, _I32, C.POINTER(SelectRow), _I32, _VP, _VP, _VP, _VP, _VP]),
     "mcr_first_year_rates": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP]),
+    "mcr_years_to_ruin": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
     "mcr_minmax": (C.c_int, [_VP, _VP, _VP, _I64, _D, _VP, _VP]),
     "mcr_histogram": (C.c_int, [_VP, _VP, _VP, _I64, _D, _I32, _I32, _VP, _VP, _VP]),
     "mcr_gather_columns": (C.c_int, [_VP, _VP, _I64, _I32, C.POINTER(_I64), _I32, _VP, _VP]),
@@ -230,6 +234,14 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.mcr_launch_count(self.handle))
 
+    @property
+    def last_variant(self) -> int:
+        return int(self.lib.mcr_last_variant(self.handle))
+
+    @property
+    def small_returns_bound(self) -> float:
+        return float(self.lib.mcr_small_returns_bound(self.handle))
+
     # ---- timeline -------------------------------------------------------------------------
     def simulate(self, seed_stream: int, working_months: int, first_path: int, n_paths: int, out: Outputs,
                  strict: bool = False) -> None:
@@ -237,9 +249,10 @@ class Context:
                                           FLAG_STRICT if strict else 0, C.byref(out), _stream_handle()))
 
     def replay(self, shocks, shocks_ld: int, n_months: int, working_months: int, n_paths: int, out: Outputs,
-               strict: bool = True) -> None:
+               strict: bool = True, small_returns: bool = False) -> None:
+        flags = (FLAG_STRICT if strict else 0) | (FLAG_SMALL_RETURNS if small_returns and not strict else 0)
         self._check(self.lib.mcr_replay(self.handle, _ptr(shocks), shocks_ld, n_months, working_months, n_paths,
-                                        FLAG_STRICT if strict else 0, C.byref(out), _stream_handle()))
+                                        flags, C.byref(out), _stream_handle()))
 
     def single_path(self, working_months: int, shocks_np):
         import numpy as np
@@ -425,6 +438,9 @@ class Context:
     def first_year_rates(self, start, fy_real, n: int, rates) -> None:
         self._check(self.lib.mcr_first_year_rates(self.handle, _ptr(start), _ptr(fy_real), n, _ptr(rates),
                                                   _stream_handle()))
+
+    def years_to_ruin(self, ruin, n: int, years) -> None:
+        self._check(self.lib.mcr_years_to_ruin(self.handle, _ptr(ruin), n, _ptr(years), _stream_handle()))
 
     def minmax(self, values, n: int, out2, mask=None, divisor: float = 1.0) -> None:
         self._check(self.lib.mcr_minmax(self.handle, _ptr(values), _ptr(mask), n, divisor, _ptr(out2),

@@ -170,10 +170,11 @@ class DeviceBatch:
 
     def years_to_ruin_into(self, dst) -> None:
         """dst[i] = ruin month / 12, NaN for paths that never failed — the reference's
-        `YearsToRuin` column (simulation.py:825-828,943), filled on the device."""
-        dst.copy_(self.ruin)
-        dst.div_(float(MONTHS_PER_YEAR))
-        dst.masked_fill_(self.ruin < 0, float("nan"))
+        `YearsToRuin` column (simulation.py:825-828,943), filled on the device by one kernel with
+        an IEEE division (a torch `div_` by a Python scalar multiplies by 1/12 instead, which is
+        1 ulp off CPython's `m / 12` for a third of the months)."""
+        assert dst.is_contiguous() and dst.numel() == self.n
+        self.ctx.years_to_ruin(self.ruin, self.n, dst)
 
 
 class DeviceAggregates:
@@ -406,9 +407,12 @@ class RetirementMonteCarloSimulator:
         return host.to(self._torch_device(), non_blocking=True), n_rows
 
     def run_batch_device(self, working_months: int, num_simulations: int, *, first_path: int = 0,
-                         series: bool = True, shocks=None, _fast_replay: bool = False) -> DeviceBatch:
+                         series: bool = True, shocks=None, _fast_replay: bool = False,
+                         _small_returns: bool = False) -> DeviceBatch:
         """One launch of the timeline kernel for `num_simulations` paths; everything stays in HBM.
-        `shocks` (device tensor [n_months, 3, n]) forces replay of those draws."""
+        `shocks` (device tensor [n_months, 3, n]) forces replay of those draws (strict build;
+        `_fast_replay` / `_small_returns` are the tests' handles on the fast build and on its
+        MCR_FLAG_SMALL_RETURNS variant, see include/mcr.h)."""
         import torch
 
         ctx = self.native_context
@@ -454,11 +458,12 @@ class RetirementMonteCarloSimulator:
         if shocks is None and self.rng_mode == "numpy":
             shocks, _ = self._numpy_shocks_device(wm, n)
         if shocks is not None:
-            ctx.replay(shocks, int(shocks.shape[2]), int(shocks.shape[0]), wm, n, out, strict=not _fast_replay)
+            ctx.replay(shocks, int(shocks.shape[2]), int(shocks.shape[0]), wm, n, out, strict=not _fast_replay,
+                       small_returns=_small_returns)
         else:
             ctx.simulate(self._seed_stream_id(), wm, int(first_path), n, out, strict=self.strict)
         return DeviceBatch(n=n, working_months=wm, T=T, R=R, cols=cols, success=success, ruin=ruin,
-                           counters=counters, traj=traj, real=real, wr=wr, shocks=shocks)
+                           counters=counters, traj=traj, real=real, wr=wr, shocks=shocks, ctx=ctx)
 
     def _staging(self, n: int, dev):
         """Pinned host destination buffers + the copy stream."""

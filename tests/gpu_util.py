@@ -46,3 +46,17 @@ def device_batch_to_host(b):
         out["real"] = b.real.cpu().numpy().T.copy()
         out["wr"] = b.wr.cpu().numpy().T.copy()
     return out
+
+
+def small_returns_hold(sim, shocks_nrc) -> bool:
+    """Do these draws (n, rows, 3) satisfy the bound on |monthly log-return| that the engine proved
+    for the scenario's own Philox draws — the guarantee MCR_FLAG_SMALL_RETURNS asks the caller for?"""
+    bound = sim.native_context.small_returns_bound
+    if not bound > 0:
+        return False
+    r12 = np.sqrt(12.0)
+    worst = 0.0
+    for c, (mu, sg) in enumerate(((sim._inv1_mu_log, sim._inv1_sigma_log), (sim._inf_mu_log, sim._inf_sigma_log),
+                                  (sim._inv2_prem_mu_log, sim._inv2_prem_sigma_log))):
+        worst = max(worst, float(np.max(np.abs(mu / 12.0 + sg / r12 * np.asarray(shocks_nrc)[:, :, c]))))
+    return worst < bound

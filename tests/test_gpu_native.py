@@ -478,3 +478,66 @@ def test_fast_native_tracks_strict_native(cfg, wm):
     assert np.median(rel) < 1e-5 and rel.max() < 1e-3, (np.median(rel), rel.max())
     rel0 = np.abs(fast["start"] - strict["start"]) / np.maximum(strict["start"], 1.0)
     assert rel0.max() < 1e-4
+
+
+def test_concurrent_simulators_and_pipelined_reductions_do_not_share_scratch():
+    """server.py runs simulations on executor worker threads (backend/server.py:309,405): two
+    simulators at once, and one simulator whose reductions run on a side stream
+    (aggregates_device(pipeline=True)) while a search and a single-path call are enqueued on the
+    main one. Scratch is per (context, stream), so every result must equal the serial one."""
+    import threading
+
+    import torch
+
+    cfg = dict(scenarios.SYNTH_C3_VOL, num_simulations_search=4000)
+    ref = make_sim(cfg)
+    want = ref.run_aggregates(100, 60_000)
+    ref.use_search_seeds()
+    want_counts = ref.batched_success_counts(list(range(0, 120, 6)), 20_000).cpu().tolist()
+    ref.use_final_seeds()
+    shocks = ref._draw_shock_path(100 + 12 * cfg["retirement_years"], 12345)
+    want_path = ref._run_path_on_shocks(100, shocks)
+
+    results, errors = {}, []
+
+    def worker(tag):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                sim = make_sim(cfg)
+                for rep in range(3):
+                    results[(tag, rep)] = sim.run_aggregates(100, 60_000)
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    # meanwhile, on this thread: pipelined reductions racing a search and a single path
+    sim = make_sim(cfg)
+    got_counts = got_path = None
+    aggs = []
+    for rep in range(3):
+        aggs.append(sim.aggregates_device(100, 60_000, pipeline=True))
+        sim.use_search_seeds()
+        got_counts = sim.batched_success_counts(list(range(0, 120, 6)), 20_000).cpu().tolist()
+        sim.use_final_seeds()
+        got_path = sim._run_path_on_shocks(100, shocks)
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+    def same(a, b):
+        for k in ("trajectory_bands", "real_trajectory_bands", "withdrawal_rate_bands"):
+            assert np.array_equal(a[k].to_numpy(), b[k].to_numpy(), equal_nan=True), k
+        for k in ("success_count", "median_first_year_withdrawal_rate", "median_start_balance",
+                  "median_final_balance_successful", "final_balance_quantiles", "ruin_month_hist",
+                  "final_balance_hist_musd_100", "final_balance_hist_60", "withdrawal_rate_counts"):
+            assert a[k] == b[k], k
+
+    for agg in aggs:
+        same(agg.to_host(), want)
+    for key, got in results.items():
+        same(got, want)
+    assert got_counts == want_counts
+    assert got_path == want_path

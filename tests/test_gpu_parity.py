@@ -199,3 +199,103 @@ def test_fast_and_strict_builds_agree_on_replay_inputs():
         assert_close(hs["final"], hf["final"])
         assert_close(hs["traj"], hf["traj"])
         assert_close(hs["fy_real"], hf["fy_real"])
+
+
+LOWVOL_CASES = [
+    ("synth_c3", scenarios.SYNTH_C3, 240),
+    ("config_json_all_fail", scenarios.CONFIG_JSON, 120),
+    ("config_json", scenarios.CONFIG_JSON, 233),
+    ("jorge_plus_lowvol", dict(scenarios.JORGE_PLUS, inv1_returns_volatility=0.05), 75),
+    ("jorge_plus_lowvol_late", dict(scenarios.JORGE_PLUS, inv1_returns_volatility=0.05, monthly_expenses=9000), 31),
+    ("stressed_lowvol_no_tax", dict(scenarios.STRESSED, inv1_returns_volatility=0.045, monthly_expenses=6500.0), 60),
+    ("high_rates", dict(scenarios.SYNTH_C3, inv1_realized_gains_tax_rate=0.45, inv2_realized_gains_tax_rate=0.3,
+                        inv1_returns_mean=0.03, inv1_returns_volatility=0.045, monthly_expenses=7000.0), 100),
+    ("tiny_balances", dict(scenarios.SYNTH_C3, initial_balance=10.0, monthly_contribution=1.0, monthly_expenses=2.0), 24),
+]
+
+
+@pytest.mark.parametrize("name,cfg,wm", LOWVOL_CASES, ids=[c[0] for c in LOWVOL_CASES])
+def test_benchmarked_variant_meets_the_replay_gate(name, cfg, wm):
+    """The kernel variant bench.py times — fast build, bounded-return specialisation with the short
+    exp polynomial and the lean month steps — fed the REFERENCE's numpy draws (proven on the host to
+    satisfy the bound, MCR_FLAG_SMALL_RETURNS): bit-identical success flags / ruin months and
+    balances within 1e-9 relative, against the strict build AND against the CPU oracle."""
+    import torch
+
+    from gpu_util import small_returns_hold
+    from oracle import oracle as orc
+
+    n = 2048
+    o = orc.OracleSimulator(cfg)
+    o.use_final_seeds()
+    shocks = orc.shocks_for_seeds(o.p, wm, o.seeds.path_seeds(n))                  # (n, rows, 3)
+    recs, traj, real, wr = orc.run_batch(o.p, wm, shocks, n_threads=4)
+    sim = make_sim(cfg)
+    assert small_returns_hold(sim, shocks)
+    dev = torch.from_numpy(np.ascontiguousarray(shocks.transpose(1, 2, 0))).to("cuda")
+    hs = device_batch_to_host(sim.run_batch_device(wm, n, shocks=dev))
+    assert sim.native_context.last_variant in (1, 2)
+    hf = device_batch_to_host(sim.run_batch_device(wm, n, shocks=dev, _fast_replay=True, _small_returns=True))
+    variant = sim.native_context.last_variant
+    assert variant in (3, 4, 5, 6)
+    # ... which is the variant a native-draw launch of this scenario uses (what bench.py times)
+    sim.run_batch_device(wm, 256, series=False)
+    assert sim.native_context.last_variant == variant
+    want_ruin = np.where(np.isnan(recs["years_to_ruin"]), -1, np.rint(recs["years_to_ruin"] * 12)).astype(np.int32)
+    for h in (hs, hf):
+        assert np.array_equal(h["success"], recs["success"].astype(bool))
+        assert np.array_equal(h["ruin_month"], want_ruin)
+        for key, ref in (("start", recs["start_balance"]), ("final", recs["final_balance"]),
+                         ("fy_gross", recs["first_year_gross"]), ("fy_real", recs["first_year_real"]),
+                         ("infl", recs["inflation_at_ret"])):
+            assert_close(h[key], ref)
+        assert_close(h["traj"], traj)
+        assert_close(h["real"], real)
+        assert np.array_equal(np.isnan(h["wr"]), np.isnan(wr))
+        assert_close(np.nan_to_num(h["wr"]), np.nan_to_num(wr))
+    assert_close(hf["final"], hs["final"])
+    assert_close(hf["traj"], hs["traj"])
+
+
+def test_benchmarked_variant_meets_the_gate_on_its_own_draws():
+    """Same gate on the engine's own Philox draws (their tails reach further than the 2048 numpy
+    paths above): strict draws replayed by the strict build vs the fast bounded-return variant."""
+    import torch
+
+    for cfg, wm in ((scenarios.SYNTH_C3, 240), (scenarios.CONFIG_JSON, 200)):
+        n = 16384
+        strict = make_sim(cfg, strict=True)
+        fast = make_sim(cfg)
+        n_rows = wm + 12 * cfg["retirement_years"]
+        shocks = torch.empty((n_rows, 3, n), dtype=torch.float64, device="cuda")
+        strict.native_context.draw_shocks(1, 0, n, n_rows, shocks, n, strict=True)
+        hs = device_batch_to_host(strict.run_batch_device(wm, n, shocks=shocks))
+        hf = device_batch_to_host(fast.run_batch_device(wm, n, shocks=shocks, _fast_replay=True, _small_returns=True))
+        assert fast.native_context.last_variant in (3, 5)
+        assert np.array_equal(hs["success"], hf["success"])
+        assert np.array_equal(hs["ruin_month"], hf["ruin_month"])
+        for key in ("start", "final", "fy_gross", "fy_real", "infl", "traj", "real"):
+            assert_close(hf[key], hs[key])
+        assert np.array_equal(np.isnan(hf["wr"]), np.isnan(hs["wr"]))
+        assert_close(np.nan_to_num(hf["wr"]), np.nan_to_num(hs["wr"]))
+
+
+def test_years_to_ruin_column_is_exactly_the_reference_division():
+    """summary_df["YearsToRuin"] = ruin_month / 12 with an IEEE division for every month value
+    (a reciprocal multiply is 1 ulp off for a third of them)."""
+    import torch
+
+    sim = make_sim(scenarios.STRESSED)
+    b = sim.run_batch_device(0, 4096, series=False)
+    months = torch.arange(-1, 1300, dtype=torch.int32, device="cuda")
+    b.ruin = months
+    b.n = months.numel()
+    out = torch.empty(months.numel(), dtype=torch.float64, device="cuda")
+    b.years_to_ruin_into(out)
+    got = out.cpu().numpy()
+    assert np.isnan(got[0])
+    assert np.array_equal(got[1:], np.arange(0, 1300) / 12)           # bit for bit
+    df = sim.run_monte_carlo_simulations(0, 3000)[0]
+    ruin = sim._last_batch.ruin.cpu().numpy()
+    want = np.where(ruin < 0, np.nan, ruin / 12)
+    assert np.array_equal(df["YearsToRuin"].to_numpy(), want, equal_nan=True)
