@@ -82,10 +82,10 @@ inline int validate_and_derive(const mcr_params& p, DevParams& d, double* live_s
   d.algebra_ok = (d.taxed1 || d.taxed2) && (!d.taxed1 || d.rate1 <= 0.999) && (!d.taxed2 || d.rate2 <= 0.999);
   d.annual_any = (!d.use1 && d.ann1 > 0) || (!d.use2 && d.ann2 > 0);
   {
-    // |mu/12| + sigma/sqrt(12) * z_max for the three factors; Box-Muller on 32-bit uniforms gives
-    // a radius r <= sqrt(-2 ln 2^-33) = 6.77, and the inflation shock rho*n0 + rho_c*n1 of ONE pair
-    // (n0, n1) = r (cos t, sin t) is r cos(t - phi) with rho^2 + rho_c^2 = 1: bounded by r as well
-    const double zmax = 6.8;
+    // |mu/12| + sigma/sqrt(12) * z_max for the three factors; Box-Muller on a 26-bit radius
+    // uniform gives r <= sqrt(-2 ln 2^-27) = 6.12, and the inflation shock rho*n0 + rho_c*n1 of ONE
+    // pair (n0, n1) = r (cos t, sin t) is r cos(t - phi) with rho^2 + rho_c^2 = 1: bounded by r too
+    const double zmax = 6.2;
     const double b1 = std::fabs(d.mu1) + d.sg1 * zmax, bi = std::fabs(d.muI) + d.sgI * zmax,
                  bp = std::fabs(d.muP) + d.sgP * zmax;
     const double worst = std::max(b1, std::max(bi, bp));
@@ -102,6 +102,8 @@ inline int validate_and_derive(const mcr_params& p, DevParams& d, double* live_s
     // need <= E * level must stay below 1e8 for the 12 months a yearly check covers (|monthly
     // log-return| < 0.1); huge needs could trip the reference's net-cash test by rounding alone
     d.lean_level_max = d.E > 0.0 ? 1e8 / (d.E * std::exp(1.2)) : 1e300;
+    d.hrate1 = 0.5 * d.rate1;
+    d.hrate2 = 0.5 * d.rate2;
   }
   d.R = p.retirement_years;
   int live = 0;

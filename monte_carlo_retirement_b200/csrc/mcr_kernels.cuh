@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_timeline(const __gri
     } else {
       const uint64_t gp = (uint64_t)(A.first_path + i);
       PhiloxShock<FAST> sh{A.keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
-                           P.rho_f, P.rho_c_f, P.rho, P.rho_c};
+                           P.rho_f, P.rho_c_f, P.rho, P.rho_c, 0.f, 0.f, 0.f};
       run_timeline<FAST, C>(P, A.wm, A.window, sh, sink, o, years_observed);
     }
   }
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_
     NullSink sink;
     const uint64_t gp = (uint64_t)(A.first_path + i);
     PhiloxShock<FAST> sh{A.keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
-                         P.rho_f, P.rho_c_f, P.rho, P.rho_c};
+                         P.rho_f, P.rho_c_f, P.rho, P.rho_c, 0.f, 0.f, 0.f};
     run_timeline<FAST, C>(P, A.wm[c], A.window + (size_t)c * 2 * MCR_MAX_STREAMS, sh, sink, o, years_observed);
   }
   const uint32_t lane = threadIdx.x & 31u;
@@ -124,7 +124,7 @@ __global__ void k_draw_shocks(const __grid_constant__ DevParams P, const __grid_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_paths) return;
   const uint64_t gp = (uint64_t)(first_path + i);
-  PhiloxShock<FAST> sh{keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, seed_stream, P.rho_f, P.rho_c_f, P.rho, P.rho_c};
+  PhiloxShock<FAST> sh{keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, seed_stream, P.rho_f, P.rho_c_f, P.rho, P.rho_c, 0.f, 0.f, 0.f};
   for (int m = 0; m < n_months; ++m) {
     double ze, zi, zp;
     sh.next(ze, zi, zp);

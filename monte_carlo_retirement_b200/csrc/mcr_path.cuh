@@ -51,6 +51,7 @@ struct DevParams {
   double lean_cg;          // 0.5 * (1 - max biting rate) * exp(-0.2): W * lean_cg > E * level  =>  need < cap / 2
   double lean_guard0;      // kLeanMinW * lean_cg (folded into the same comparison)
   double lean_level_max;   // yearly check: E * level stays < 1e8 for the next 12 months
+  double hrate1, hrate2;   // rate / 2: max(0, g) * rate == (g + |g|) * (rate / 2) exactly
   DevStream streams[MCR_MAX_STREAMS];
 };
 
@@ -560,6 +561,12 @@ struct Factors {
   double G1, GI, GP;
 };
 
+// max(0, gain) * rate as (gain + |gain|) * (rate / 2): the same value bit for bit (the sum is
+// exactly 2 * max(0, gain), the halved rate only shifts the exponent), but two FP64-pipe
+// instructions instead of a compare and two 32-bit selects — the selects issue on the half-rate
+// integer / FP32 datapath that bounds this kernel on B200, the FP64 pipe has slack.
+MCR_DEV double latent_tax(double gain, double half_rate) { return (gain + fabs(gain)) * half_rate; }
+
 // The rebalance of a portfolio (nb1, nb2) with cost bases (c1, c2) that is guaranteed to trade
 // without clamps: returns the fraction-sold bookkeeping applied to the cost bases and the total
 // after the sale's tax, V - fs * tx_s (simulation.py:298-353 solved in closed form).
@@ -594,8 +601,8 @@ MCR_DEV void lean_accumulate(const DevParams& P, const Factors& cur, double k1, 
   level *= cur.GI;
   const double V = nb1 + nb2;
   double c1 = cb1 + k1, c2 = cb2 + k2;
-  const double tx1 = C::taxed1(P) ? pmax(0.0, nb1 - c1) * P.rate1 : 0.0;
-  const double tx2 = C::taxed2(P) ? pmax(0.0, nb2 - c2) * P.rate2 : 0.0;
+  const double tx1 = C::taxed1(P) ? latent_tax(nb1 - c1, P.hrate1) : 0.0;
+  const double tx2 = C::taxed2(P) ? latent_tax(nb2 - c2, P.hrate2) : 0.0;
   const double Wn = lean_rebalance<C>(P, nb1, nb2, V, tx1, tx2, c1, c2);
   cb1 = c1;
   cb2 = c2;
@@ -605,21 +612,22 @@ MCR_DEV void lean_accumulate(const DevParams& P, const Factors& cur, double k1, 
 }
 
 // retirement month — simulation.py:644-796 (cnet = E - sum(indexed amount * (1 - tax)), fixed = sum of the locked
-// nominal non-indexed payments * (1 - tax): need = max(0, cnet * level - fixed))
+// nominal non-indexed payments * (1 - tax): need = max(0, cnet * level - fixed); the caller passes both halved)
 template <class C>
-MCR_DEV void lean_decumulate(const DevParams& P, const Factors& cur, double cnet, double fixed, double level_ret,
+MCR_DEV void lean_decumulate(const DevParams& P, const Factors& cur, double cnet_h, double fixed_h, double level_ret,
                              double& b1, double& cb1, double& b2, double& cb2, double& level, double& yr_gross,
                              double& yr_real, bool& bal) {
   const double level0 = level;
-  const double need = pmax(0.0, fma(cnet, level0, -fixed));
+  const double half_need = fma(cnet_h, level0, -fixed_h);   // (E*level - income) / 2, exactly
+  const double need = half_need + fabs(half_need);          // max(0, E*level - income) (:679-682)
   const double G2 = cur.GI * cur.GP;
   const double nb1 = b1 * cur.G1;
   const double nb2 = b2 * G2;
   const double lv = level0 * cur.GI;
   const double V = nb1 + nb2;
   double c1 = cb1, c2 = cb2;
-  const double tx1 = C::taxed1(P) ? pmax(0.0, nb1 - c1) * P.rate1 : 0.0;   // tax due on full liquidation
-  const double tx2 = C::taxed2(P) ? pmax(0.0, nb2 - c2) * P.rate2 : 0.0;
+  const double tx1 = C::taxed1(P) ? latent_tax(nb1 - c1, P.hrate1) : 0.0;   // tax due on full liquidation
+  const double tx2 = C::taxed2(P) ? latent_tax(nb2 - c2, P.hrate2) : 0.0;
   double gross, q;
   if constexpr (C::kAnyTaxed) {
     // both withdrawals at once (:750-777): net target split by w_i = cap_i / cap and grossed up by
@@ -761,8 +769,10 @@ MCR_DEV void run_timeline(const DevParams& P, const int wm,
   double lockn[MCR_MAX_STREAMS];
   uint32_t lockn_mask = 0;
   const int ns = P.n_streams;
-  double idx_coeff = 0.0, fixed_income = 0.0;  // fast build: cached stream sums
-  [[maybe_unused]] double cnet = P.E;          // lean months: E - idx_coeff
+  // fast build: cached stream sums between two window boundaries, kept HALVED (exact scaling):
+  // need = max(0, E*level - income) = t + |t| with t = cnet_h * level - fixed_h
+  [[maybe_unused]] double cnet_h = 0.5 * P.E;  // (E - sum of indexed amount * (1 - tax)) / 2
+  [[maybe_unused]] double fixed_h = 0.0;       // (sum of locked nominal payments * (1 - tax)) / 2
   int next_event = 0;                          // next retirement month at which they change
   if constexpr (kLean) bal = !pre_fail && lean_ready(P, b1, b2, level, true);
   double fy_gross = 0.0, fy_real = 0.0;
@@ -788,8 +798,7 @@ MCR_DEV void run_timeline(const DevParams& P, const int wm,
         // between two boundaries net income = level * sum(indexed amount*(1-tax)) + sum(locked
         // nominal*(1-tax)), one DFMA per month. The sums are rebuilt at a boundary month.
         if (__builtin_expect(r == next_event, 0)) {
-          idx_coeff = 0.0;
-          fixed_income = 0.0;
+          double idx_coeff = 0.0, fixed_income = 0.0;
           int nxt_ev = 0x7fffffff;
           for (int k = 0; k < ns; ++k) {
             const int first = window[2 * k], end = window[2 * k + 1];
@@ -805,7 +814,8 @@ MCR_DEV void run_timeline(const DevParams& P, const int wm,
             }
           }
           next_event = nxt_ev;
-          cnet = P.E - idx_coeff;
+          cnet_h = 0.5 * (P.E - idx_coeff);
+          fixed_h = 0.5 * fixed_income;
         }
         if constexpr (kLean) {
           if (__builtin_expect(bal, 1)) {
@@ -813,7 +823,7 @@ MCR_DEV void run_timeline(const DevParams& P, const int wm,
             double ze, zi, zp;
             shock.next(ze, zi, zp);                                // draws of the FOLLOWING month
             ++executed;
-            lean_decumulate<C>(P, cur, cnet, fixed_income, level_ret, b1, cb1, b2, cb2, level, yr_g1, yr_real, bal);
+            lean_decumulate<C>(P, cur, cnet_h, fixed_h, level_ret, b1, cb1, b2, cb2, level, yr_g1, yr_real, bal);
             MCR_COUNT_LEAN_MONTH();
             Math<FAST>::template factors<C>(P, ze, zi, zp, nxt.G1, nxt.GI, nxt.GP);
             // the month cannot fail, and the (empty) annual-tax event at a tax-year end reduces to
@@ -822,7 +832,6 @@ MCR_DEV void run_timeline(const DevParams& P, const int wm,
             continue;
           }
         }
-        income = idx_coeff * level0 + fixed_income;
       } else {
         if (ns > 0) stream_income(P.streams[0], window[0], window[1], r, level0, lock0, locked0, income);
         if (ns > 1) stream_income(P.streams[1], window[2], window[3], r, level0, lock1, locked1, income);
@@ -834,8 +843,14 @@ MCR_DEV void run_timeline(const DevParams& P, const int wm,
           if (lk && !was) { lockn[k] = lv; lockn_mask |= 1u << k; }
         }
       }
-      const double need_nominal = P.E * level0;
-      const double need = pmax(0.0, need_nominal - income);        // :679-682
+      double need;                                                 // :679-682
+      if constexpr (FAST) {
+        const double t = fma(cnet_h, level0, -fixed_h);
+        need = pmax(0.0, t + t);
+      } else {
+        const double need_nominal = P.E * level0;
+        need = pmax(0.0, need_nominal - income);
+      }
       const bool wants = need > kEps;
       if (__builtin_expect(b1 + b2 <= kEps && wants, 0)) { failed = true; break; }  // :684-690
 

@@ -369,19 +369,21 @@ template <bool MASKED, int MODE>
 __device__ __forceinline__ void collect_elements(const Probe& P, const double* __restrict__ x,
                                                  const uint8_t* __restrict__ m, int cnt, SelRow& R,
                                                  double* __restrict__ out, unsigned long long* s_min,
-                                                 unsigned long long* s_max, const int* s_big, int* s_full) {
+                                                 unsigned long long* s_max, const int* s_big) {
   scan_elements<kHistThreads, MASKED>(x, m, cnt, [&](bool ok, double v, uint32_t hi, uint32_t lo) {
     if (!ok) return;
     const int g = group_of<MODE>(P, hi, lo);
     if (g < 0) return;
-    // bucket extremes (shared-memory atomics, merged once per CTA): a bucket of one repeated
-    // value is recognised later by min == max
+    // bucket extremes (shared-memory atomics only — no plain read races them —, merged once per
+    // CTA): a bucket of one repeated value is recognised later by min == max. Few elements get
+    // here: the live buckets are small by now, except for repeated values (zero-padded failures).
     const unsigned long long k = ((unsigned long long)hi << 32) | lo;
-    if (k < *(volatile unsigned long long*)&s_min[g]) atomicMin(&s_min[g], k);
-    if (k > *(volatile unsigned long long*)&s_max[g]) atomicMax(&s_max[g], k);
-    if (!s_big[g] && !*(volatile int*)s_full) {
+    atomicMin(&s_min[g], k);
+    atomicMax(&s_max[g], k);
+    if (!s_big[g]) {
+      // an overflowing list is detected from n_cand by k_sel_collect_finish
       const int at = atomicAdd(&R.n_cand, 1);
-      if (at < kCandCap) out[at] = v; else *s_full = 1;
+      if (at < kCandCap) out[at] = v;
     }
   });
 }
@@ -389,7 +391,6 @@ __device__ __forceinline__ void collect_elements(const Probe& P, const double* _
 __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand) {
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
-  __shared__ int s_full;
   __shared__ int s_big[kMaxTargets];
   SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
@@ -401,7 +402,6 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
     s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull;
     s_big[threadIdx.x] = threadIdx.x < ng ? R.gbig[threadIdx.x] : 0;
   }
-  if (threadIdx.x == 0) s_full = 0;
   if (rb > 0) build_table(T, R, ng, rb); else __syncthreads();
   const int64_t begin = (int64_t)blockIdx.x * kChunk;
   const int cnt = (int)(begin + kChunk < n ? kChunk : n - begin);
@@ -410,21 +410,20 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
   double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
   const Probe P = make_probe(R, rb, 0, T, nullptr);
   if (rb == 0) {
-    if (m) collect_elements<true, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
-    else collect_elements<false, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+    if (m) collect_elements<true, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big);
+    else collect_elements<false, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big);
   } else if (ng == 1) {
-    if (m) collect_elements<true, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
-    else collect_elements<false, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+    if (m) collect_elements<true, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big);
+    else collect_elements<false, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big);
   } else {
-    if (m) collect_elements<true, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
-    else collect_elements<false, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big, &s_full);
+    if (m) collect_elements<true, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big);
+    else collect_elements<false, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big);
   }
   __syncthreads();
   if (threadIdx.x < ng && s_min[threadIdx.x] != ~0ull) {
     atomicMin((unsigned long long*)&R.gmin[threadIdx.x], s_min[threadIdx.x]);
     atomicMax((unsigned long long*)&R.gmax[threadIdx.x], s_max[threadIdx.x]);
   }
-  if (threadIdx.x == 0 && s_full) R.overflow = 1;
 }
 
 // Row extremes <-> a caller buffer ext[rows][2] of int64 in an order-preserving signed encoding
@@ -680,7 +679,7 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
     __syncthreads();
     if (tid < nt) {
       const int g = R.group[tid];
-      if (R.gbig[g] ? (R.gmin[g] != R.gmax[g]) : (R.overflow != 0)) need_scan = 1;
+      if (R.gbig[g] ? (R.gmin[g] != R.gmax[g]) : (R.overflow != 0)) atomicOr(&need_scan, 1);
     }
     __syncthreads();
     if (!need_scan) {

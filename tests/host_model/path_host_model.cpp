@@ -119,7 +119,7 @@ int hm_draw(const mcr_params* params, uint64_t main_seed, uint32_t seed_stream, 
   philox_expand_keys(k0, k1, keys);
   for (int64_t i = 0; i < n; ++i) {
     const uint64_t gp = (uint64_t)(first_path + i);
-    PhiloxShock<false> sh{keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, seed_stream, P.rho_f, P.rho_c_f, P.rho, P.rho_c};
+    PhiloxShock<false> sh{keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, seed_stream, P.rho_f, P.rho_c_f, P.rho, P.rho_c, 0.f, 0.f, 0.f};
     for (int m = 0; m < n_months; ++m) {
       double ze, zi, zp;
       sh.next(ze, zi, zp);

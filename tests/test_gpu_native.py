@@ -14,76 +14,27 @@ pytestmark = pytest.mark.gpu
 
 
 # ---------------------------------------------------------------------------------------------
-# Philox + normals
+# Philox + normals (the numpy restatement lives in tests/philox_ref.py; its Random123 KAT and the
+# distribution of the draw layout are checked on the CPU in tests/test_host_model.py)
 # ---------------------------------------------------------------------------------------------
-def _philox4x32_10(c, k):
-    """numpy restatement of Philox4x32-10 (Salmon et al. 2011) on arrays of counters."""
-    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
-    c0, c1, c2, c3 = [x.astype(np.uint32) for x in c]
-    k0 = np.uint32(k[0])
-    k1 = np.uint32(k[1])
-    with np.errstate(over="ignore"):
-        for _ in range(10):
-            p0 = M0 * c0.astype(np.uint64)
-            p1 = M1 * c2.astype(np.uint64)
-            n0 = (p1 >> np.uint64(32)).astype(np.uint32) ^ c1 ^ k0
-            n2 = (p0 >> np.uint64(32)).astype(np.uint32) ^ c3 ^ k1
-            c1 = p1.astype(np.uint32)
-            c3 = p0.astype(np.uint32)
-            c0, c2 = n0, n2
-            k0 = np.uint32((int(k0) + int(W0)) & 0xFFFFFFFF)
-            k1 = np.uint32((int(k1) + int(W1)) & 0xFFFFFFFF)
-    return c0, c1, c2, c3
-
-
-def test_philox_known_answer_vectors():
-    """Random123 KAT: the numpy restatement used below to check the device stream is Philox."""
-    z = np.zeros(1, dtype=np.uint32)
-    out = _philox4x32_10((z, z, z, z), (0, 0))
-    assert [int(x[0]) for x in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
-    f = np.full(1, 0xFFFFFFFF, dtype=np.uint32)
-    out = _philox4x32_10((f, f, f, f), (0xFFFFFFFF, 0xFFFFFFFF))
-    assert [int(x[0]) for x in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
-
-
-def _splitmix64(x):
-    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-    return x ^ (x >> 31)
-
-
 def test_device_shocks_are_philox_box_muller():
-    """mcr_draw_shocks == Philox4x32-10(key(main_seed); path, month, stream) + Box-Muller."""
+    """mcr_draw_shocks == Philox4x32-10(key(main_seed); path, month / 2, stream) + three Box-Muller
+    pairs per call (csrc/mcr_rng.cuh), for both arithmetic builds."""
     import torch
+
+    import philox_ref
 
     cfg = dict(scenarios.SYNTH_C3, equity_inflation_correlation=-0.5)
     sim = make_sim(cfg, strict=True)
-    n, months, first = 257, 40, 1_000_000_007
-    sh = torch.empty((months, 3, n), dtype=torch.float64, device="cuda")
-    sim.native_context.draw_shocks(1, first, n, months, sh, n, strict=True)
-    got = sh.cpu().numpy()
-    key = _splitmix64(_splitmix64(sim.main_seed) ^ 0x6D63725F62323030)
-    paths = (first + np.arange(n, dtype=np.uint64))
-    p_lo = np.repeat((paths & np.uint64(0xFFFFFFFF)).astype(np.uint32)[None, :], months, 0)
-    p_hi = np.repeat((paths >> np.uint64(32)).astype(np.uint32)[None, :], months, 0)
-    mm = np.repeat(np.arange(months, dtype=np.uint32)[:, None], n, 1)
-    r = _philox4x32_10((p_lo, p_hi, mm, np.full_like(mm, 1)), (key & 0xFFFFFFFF, key >> 32))
-
-    def bm(a, b):
-        u1 = (a.astype(np.float64) + 0.5) / 2.0**32
-        th = (b.astype(np.float64) + 0.5) / 2.0**31 - 1.0
-        rr = np.sqrt(-2.0 * np.log(u1))
-        return rr * np.cos(np.pi * th), rr * np.sin(np.pi * th)
-
-    n0, n1 = bm(r[0], r[1])
-    n2, _ = bm(r[2], r[3])
-    rho = -0.5
-    want = np.stack([n0, rho * n0 + math.sqrt(1 - rho * rho) * n1, n2], axis=1)
-    assert np.max(np.abs(got - want)) < 5e-5  # fp32 transform on the device
-    # the fast build (MUFU lg2/sin/cos) draws the same normals to ~1e-5
-    sim.native_context.draw_shocks(1, first, n, months, sh, n, strict=False)
-    assert np.max(np.abs(sh.cpu().numpy() - want)) < 2e-4
+    for n, months, first in ((257, 41, 1_000_000_007), (64, 6, (1 << 33) + 5)):
+        sh = torch.empty((months, 3, n), dtype=torch.float64, device="cuda")
+        sim.native_context.draw_shocks(1, first, n, months, sh, n, strict=True)
+        got = sh.cpu().numpy()
+        want = philox_ref.shocks(sim.main_seed, 1, first, n, months, -0.5)
+        assert np.max(np.abs(got - want)) < 5e-5  # fp32 transform on the device
+        # the fast build (MUFU lg2/sin/cos) draws the same normals to ~1e-5
+        sim.native_context.draw_shocks(1, first, n, months, sh, n, strict=False)
+        assert np.max(np.abs(sh.cpu().numpy() - want)) < 2e-4
 
 
 def test_native_shock_distribution():
@@ -462,7 +413,7 @@ def test_large_batch_aggregate_only_mode():
     assert 99.0 < h["success_probability"] < 100.0
 
 
-@pytest.mark.parametrize("cfg,wm", [(scenarios.SYNTH_C3, 240), (scenarios.TEST_BASE, 36), (scenarios.TAX_HEAVY, 120)],
+@pytest.mark.parametrize("cfg,wm", [(scenarios.SYNTH_C3, 240), (scenarios.TEST_BASE, 36), (scenarios.TAX_HEAVY, 260)],
                          ids=["c3_small_exp", "no_tax", "generic"])
 def test_fast_native_tracks_strict_native(cfg, wm):
     """Throughput build with its own draws (MUFU normals, short exp polynomial when the host
@@ -474,6 +425,7 @@ def test_fast_native_tracks_strict_native(cfg, wm):
     strict = device_batch_to_host(make_sim(cfg, strict=True).run_batch_device(wm, n))
     assert (fast["success"] != strict["success"]).mean() < 2e-4
     both = fast["success"] & strict["success"]
+    assert both.sum() > 100   # (TAX_HEAVY succeeds on ~6 % of the paths at 260 working months)
     rel = np.abs(fast["final"][both] - strict["final"][both]) / np.maximum(strict["final"][both], 1.0)
     assert np.median(rel) < 1e-5 and rel.max() < 1e-3, (np.median(rel), rel.max())
     rel0 = np.abs(fast["start"] - strict["start"]) / np.maximum(strict["start"], 1.0)
@@ -540,4 +492,6 @@ def test_concurrent_simulators_and_pipelined_reductions_do_not_share_scratch():
     for key, got in results.items():
         same(got, want)
     assert got_counts == want_counts
-    assert got_path == want_path
+    assert got_path.keys() == want_path.keys()
+    for k in want_path:   # the withdrawal-rate list of a failing path carries NaN
+        assert np.array_equal(np.asarray(got_path[k], dtype=float), np.asarray(want_path[k], dtype=float), equal_nan=True), k

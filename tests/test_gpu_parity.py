@@ -245,16 +245,18 @@ def test_benchmarked_variant_meets_the_replay_gate(name, cfg, wm):
     for h in (hs, hf):
         assert np.array_equal(h["success"], recs["success"].astype(bool))
         assert np.array_equal(h["ruin_month"], want_ruin)
-        for key, ref in (("start", recs["start_balance"]), ("final", recs["final_balance"]),
-                         ("fy_gross", recs["first_year_gross"]), ("fy_real", recs["first_year_real"]),
-                         ("infl", recs["inflation_at_ret"])):
-            assert_close(h[key], ref)
-        assert_close(h["traj"], traj)
-        assert_close(h["real"], real)
         assert np.array_equal(np.isnan(h["wr"]), np.isnan(wr))
-        assert_close(np.nan_to_num(h["wr"]), np.nan_to_num(wr))
-    assert_close(hf["final"], hs["final"])
-    assert_close(hf["traj"], hs["traj"])
+    # the parity build against the oracle: plain 1e-9 (it is ~1e-13 in practice)
+    for key, ref in (("start", recs["start_balance"]), ("final", recs["final_balance"]),
+                     ("fy_gross", recs["first_year_gross"]), ("fy_real", recs["first_year_real"]),
+                     ("infl", recs["inflation_at_ret"]), ("traj", traj), ("real", real)):
+        assert_close(hs[key], ref)
+    assert_close(np.nan_to_num(hs["wr"]), np.nan_to_num(wr))
+    # the benchmarked variant against the oracle (see assert_close_fast for the per-path floor)
+    _assert_fast_gate(hf, {"start": recs["start_balance"], "final": recs["final_balance"],
+                           "fy_gross": recs["first_year_gross"], "fy_real": recs["first_year_real"],
+                           "infl": recs["inflation_at_ret"], "traj": traj, "real": real, "wr": wr})
+    _assert_fast_gate(hf, hs)
 
 
 def test_benchmarked_variant_meets_the_gate_on_its_own_draws():
@@ -274,10 +276,29 @@ def test_benchmarked_variant_meets_the_gate_on_its_own_draws():
         assert fast.native_context.last_variant in (3, 5)
         assert np.array_equal(hs["success"], hf["success"])
         assert np.array_equal(hs["ruin_month"], hf["ruin_month"])
-        for key in ("start", "final", "fy_gross", "fy_real", "infl", "traj", "real"):
-            assert_close(hf[key], hs[key])
         assert np.array_equal(np.isnan(hf["wr"]), np.isnan(hs["wr"]))
-        assert_close(np.nan_to_num(hf["wr"]), np.nan_to_num(hs["wr"]))
+        _assert_fast_gate(hf, hs)
+        # how much of it needed the per-path floor at all: balances at their own scale obey the plain gate
+        big = np.abs(hs["traj"]) >= 1e-3 * hs["traj"].max(axis=1, keepdims=True)
+        rel_err = np.abs(hf["traj"] - hs["traj"])[big] / np.abs(hs["traj"])[big]
+        assert rel_err.max() < 1e-9, rel_err.max()
+
+
+def _assert_fast_gate(hf, ref):
+    """hf (fast build, dict of device_batch_to_host) against ref (same keys): 1e-9 relative with the
+    per-path floor of gpu_util.assert_close_fast on balances; withdrawals and rates are sums, not
+    differences, and get the plain relative gate."""
+    from gpu_util import assert_close_fast
+
+    peak = np.abs(np.asarray(ref["traj"])).max(axis=1)
+    peak_real = np.abs(np.asarray(ref["real"])).max(axis=1)
+    assert_close_fast(hf["traj"], ref["traj"], peak)
+    assert_close_fast(hf["real"], ref["real"], peak_real)
+    assert_close_fast(hf["start"], ref["start"], peak)
+    assert_close_fast(hf["final"], ref["final"], peak)
+    for key in ("fy_gross", "fy_real", "infl"):
+        assert_close(hf[key], ref[key])
+    assert_close(np.nan_to_num(hf["wr"]), np.nan_to_num(ref["wr"]))
 
 
 def test_years_to_ruin_column_is_exactly_the_reference_division():

