@@ -66,6 +66,18 @@ class Collectives:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def barrier(self) -> None:
+        """All ranks have reached this point AND their previously enqueued device work is done."""
+        import torch
+
+        if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl":
+            torch.cuda.current_stream().synchronize()
+        self.dist.barrier(group=self.group)
+
+    def broadcast0_(self, t):
+        self.dist.broadcast(t, src=0, group=self.group)
+        return t
+
     def gather_cat(self, t, dim: int = -1, sizes: Optional[Sequence[int]] = None):
         """Concatenate the ranks' shards along `dim`. `sizes` (every rank's extent along dim) avoids
         an object all-gather when the caller can compute it (shard_range)."""
@@ -98,10 +110,8 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         super().__init__(params_model, main_seed_override, **kw)
         self.coll = collectives or Collectives()
         self._agreed: Dict[Any, int] = {}
-        self._select_flag = None
-        self._stepwise_only = False
-        self.select_fallbacks = 0
         self._sign4 = None
+        self._shared_blocks: List["_SharedSummaryBlock"] = []   # rank-0-visible summary blocks (host, pinned)
         if self.rng_mode != "philox":
             raise ValueError("sharding needs the counter-based Philox draws (rng='philox')")
 
@@ -130,40 +140,17 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
             self._agreed[key] = out
         return out
 
-    def _select(self, specs, out16, counts=None) -> None:
+    def _select(self, specs, out16, counts=None, stepwise: bool = False):
         # exact GLOBAL order statistics: local digit histograms all-reduced per pass, then the few
-        # candidates left are pooled across ranks (the "could not finish" count is checked at the
-        # caller's next host sync: _selects_ok)
+        # candidates left are pooled across ranks. The pooled tail reports rows it could not finish
+        # in a device flag (identical on every rank) that the caller checks at its next host sync
+        # and answers with `stepwise=True` on the still-resident rows.
         ctx, coll = self.native_context, self.coll
-        if self._stepwise_only:
+        if stepwise:
             ctx.quantiles_rows(specs, out16, counts=counts, all_reduce=coll.sum_, all_reduce_min=coll.min_)
-            return
-        flag = ctx.quantiles_rows(specs, out16, counts=counts, all_reduce=coll.sum_, all_reduce_min=coll.min_,
+            return None
+        return ctx.quantiles_rows(specs, out16, counts=counts, all_reduce=coll.sum_, all_reduce_min=coll.min_,
                                   rank=coll.rank, world=coll.world, defer_check=True)
-        if flag is not None:
-            import torch
-
-            self._select_flag = flag if self._select_flag is None else torch.maximum(self._select_flag, flag)
-
-    def _selects_ok(self) -> bool:
-        flag, self._select_flag = self._select_flag, None
-        ok = flag is None or int(flag.item()) == 0
-        if not ok:
-            self.select_fallbacks += 1  # reported by bench.py: a fallback re-runs work outside a timed loop
-        return ok
-
-    def _stepwise_selects(self):
-        import contextlib
-
-        @contextlib.contextmanager
-        def forced():
-            before, self._stepwise_only = self._stepwise_only, True
-            try:
-                yield
-            finally:
-                self._stepwise_only = before
-
-        return forced()
 
     def _reduce_samples(self, block):
         return self.coll.sum_(block)
@@ -188,65 +175,184 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
         coll.sum_(hists)
 
-    # ---- the reference's 7-tuple, global, on every rank ------------------------------------------
+    # ---- the reference's 7-tuple ------------------------------------------------------------------
     def run_monte_carlo_simulations(self, working_months: int, num_simulations: int):
+        """simulation.py:952-1128 over W ranks. Every rank returns the GLOBAL band frames, sample
+        paths and observation counts. `summary_df` (N rows x 7 columns, the only N-sized output):
+        rank 0 gets all N_global rows, the other ranks the rows of their own shard.
+
+        No per-path data crosses NVLink: every GPU copies ITS OWN shard of the seven columns over
+        ITS OWN PCIe link — underneath the select kernels — into one host block that all ranks of
+        the box map (POSIX shared memory, page-locked in every process), at the offset of its global
+        path range; rank 0's DataFrame is a zero-copy view of that block. (Round 1 all-gathered the
+        columns to every GPU and copied all N rows to the host on every rank: 8 x 448 MB per call
+        at 8 GPUs, 55.7 ms; this is 8 x 56 MB in parallel.)"""
         import torch
 
         coll = self.coll
         n_global = int(num_simulations)
+        if n_global <= 0:
+            return super().run_monte_carlo_simulations(working_months, n_global)
         lo, n = shard_range(n_global, coll.rank, coll.world)
         b = self.run_batch_device(working_months, n, series=True, first_path=lo)
         dev = b.cols.device
         T, R = b.T, b.R
         nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
         f64 = dict(dtype=torch.float64, device=dev)
+
+        # ---- the shard's columns start their trip to the host as soon as the timeline kernel is done
+        main = torch.cuda.current_stream()
+        years = torch.empty(n, **f64)
+        b.years_to_ruin_into(years)
+        produced = torch.cuda.Event()
+        produced.record(main)
+        block = self._summary_block(n_global)          # collective: rank 0 picks a free generation
+        stage = self._staging(n, dev) if coll.rank != 0 else None   # private copy backing this rank's own frame
+        copy_stream = self._copy_stream if stage is None else stage["stream"]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(produced)
+            for c in range(5):
+                block.cols[c, lo:lo + n].copy_(b.cols[c], non_blocking=True)
+            block.cols[5, lo:lo + n].copy_(years, non_blocking=True)
+            block.succ[lo:lo + n].copy_(b.success, non_blocking=True)
+            if stage is not None:
+                stage["cols"][:5].copy_(b.cols, non_blocking=True)
+                stage["cols"][5].copy_(years, non_blocking=True)
+                stage["succ"].copy_(b.success, non_blocking=True)
+        years.record_stream(copy_stream)
+
+        # ---- global bands (one distributed multi-row select) and the sample paths
         bands = torch.empty((T, nq), **f64)
         real_bands = torch.empty((T, nq), **f64)
         wr_bands = torch.empty((R, nw), **f64)
         wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-        self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)  # one distributed multi-row select
-        # sample paths: each rank contributes the columns it owns, summed into a zero block
+        flag = self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
         k = len(self._sample_columns(n_global))
-        samples = torch.zeros((2, k, T), **f64)
+        samples = torch.zeros((2, k, T), **f64)   # each rank fills the columns it owns, summed into zeros
         self._gather_samples(b.traj, n, T, lo, n_global, samples[0])
         self._gather_samples(b.real, n, T, lo, n_global, samples[1])
         self._reduce_samples(samples)
-        # summary columns of all shards, in global path order: ONE all-gather of a packed
-        # [5 f64 | success | ruin] block per rank over NVLink, one pinned D2H, zero-copy DataFrame
-        sizes = [shard_range(n_global, r, coll.world)[1] for r in range(coll.world)]
-        m = max(sizes)
-        packed = torch.zeros((7, m), **f64)
-        packed[0:5, :n] = b.cols
-        packed[5, :n] = b.success.to(torch.float64)
-        b.years_to_ruin_into(packed[6, :n])
-        gathered = torch.empty((coll.world, 7, m), **f64)
-        coll.dist.all_gather_into_tensor(gathered, packed, group=coll.group)
-        host = torch.empty((7, n_global), dtype=torch.float64, pin_memory=True)
-        if all(sz == m for sz in sizes):
-            host.copy_(gathered.permute(1, 0, 2).reshape(7, -1), non_blocking=True)
+        if flag is not None and int(flag.item()) != 0:   # rare: the pooled select gave up on a row -> stepwise protocol
+            self.select_fallbacks += 1
+            self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts, stepwise=True)
+        s = samples.cpu().numpy()                       # synchronises the main stream
+        small = [bands.cpu().numpy(), wr_bands.cpu().numpy(), real_bands.cpu().numpy(), wr_counts.cpu().numpy()]
+        copy_stream.synchronize()
+        coll.barrier()                                  # every shard has landed in the shared block
+        self.last_d2h_bytes = n * (6 * 8 + 1) * (1 if stage is None else 2) + (2 * T * nq + R * nw + 2 * k * T + R) * 8
+        if coll.rank == 0:
+            c, succ = block.np_cols, block.np_succ      # views of these keep the generation busy (is_free)
         else:
-            host.copy_(torch.cat([gathered[r, :, :sz] for r, sz in enumerate(sizes)], dim=1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        if not self._selects_ok():  # rare: the pooled select gave up on a row -> stepwise protocol
-            with self._stepwise_selects():
-                self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
-        all_cols = host.numpy()
-        self.last_d2h_bytes = n_global * 7 * 8 + (2 * T * nq + R * nw + 2 * k * T + R) * 8
+            c, succ = stage["cols"].numpy(), stage["succ"].numpy()
         summary_df = pd.DataFrame({
-            "Start Balance": all_cols[0],
-            "Final Balance": all_cols[1],
-            "Success": all_cols[5] != 0.0,
-            "YearsToRuin": all_cols[6],
-            "First Year Gross Withdrawal": all_cols[2],
-            "First Year Real Gross Withdrawal": all_cols[3],
-            "Inflation At Retirement": all_cols[4],
+            "Start Balance": c[0],
+            "Final Balance": c[1],
+            "Success": succ.view("bool"),                # 0/1 bytes written by the kernel
+            "YearsToRuin": c[5],
+            "First Year Gross Withdrawal": c[2],
+            "First Year Real Gross Withdrawal": c[3],
+            "Inflation At Retirement": c[4],
         }, copy=False)
-        s = samples.cpu().numpy()
         self._last_batch = b
         return (summary_df,
-                pd.DataFrame(bands.cpu().numpy(), columns=TRAJECTORY_QUANTILES),
+                pd.DataFrame(small[0], columns=TRAJECTORY_QUANTILES),
                 s[0].tolist(),
-                pd.DataFrame(wr_bands.cpu().numpy(), columns=WITHDRAWAL_RATE_QUANTILES),
-                pd.DataFrame(real_bands.cpu().numpy(), columns=TRAJECTORY_QUANTILES),
+                pd.DataFrame(small[1], columns=WITHDRAWAL_RATE_QUANTILES),
+                pd.DataFrame(small[2], columns=TRAJECTORY_QUANTILES),
                 s[1].tolist(),
-                [int(v) for v in wr_counts.cpu().numpy()])
+                [int(v) for v in small[3]])
+
+    def _staging(self, n: int, dev):
+        if getattr(self, "_copy_stream", None) is None:
+            import torch
+
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        return super()._staging(n, dev)
+
+    def _summary_block(self, n_global: int) -> "_SharedSummaryBlock":
+        """The host block of this call: a generation of the right size that no live DataFrame of
+        rank 0 still views, chosen by rank 0 and announced to the others (one tiny broadcast);
+        a new generation is created — shared memory + page-locking, ~0.1 s, once — when none is free."""
+        import torch
+
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self._torch_device())
+        coll = self.coll
+        pick = torch.zeros(1, dtype=torch.int64, device=self._torch_device())
+        if coll.rank == 0:
+            free = [i for i, blk in enumerate(self._shared_blocks) if blk.n == n_global and blk.is_free()]
+            pick[0] = free[0] if free else len(self._shared_blocks)
+        idx = int(coll.broadcast0_(pick).item())
+        while len(self._shared_blocks) <= idx:
+            gen = len(self._shared_blocks)
+            n_of = n_global if gen == idx else 0
+            self._shared_blocks.append(_SharedSummaryBlock(coll, self._block_tag(), gen, n_of))
+        return self._shared_blocks[idx]
+
+    def _block_tag(self) -> str:
+        import os
+
+        return f"mcr_b200_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{id(self) if self.coll.world == 1 else 0}"
+
+
+class _SharedSummaryBlock:
+    """[6][N] float64 + [N] uint8 in POSIX shared memory, mapped and page-locked by every rank of the
+    box (cudaHostRegister), so each GPU's copy engine writes its shard straight into the block rank
+    0 reads. Created by rank 0, opened by the others after a barrier, unlinked at once (the
+    mapping keeps it alive)."""
+
+    def __init__(self, coll: Collectives, tag: str, gen: int, n: int):
+        import mmap
+        import os
+        import sys
+
+        import numpy as np
+        import torch
+
+        self.n = n
+        self.coll = coll
+        if n == 0:          # placeholder generation of another size class
+            self.cols = self.succ = None
+            return
+        path = f"/dev/shm/{tag}_{gen}_{n}"
+        size = 6 * 8 * n + n
+        size = (size + 4095) // 4096 * 4096
+        if coll.rank == 0:
+            fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, size)
+        coll.barrier()
+        if coll.rank != 0:
+            fd = os.open(path, os.O_RDWR)
+        self._map = mmap.mmap(fd, size)
+        os.close(fd)
+        coll.barrier()
+        if coll.rank == 0:
+            os.unlink(path)
+        # every numpy view of the block (the columns of rank 0's DataFrame) holds a reference to
+        # `_raw`, the array that owns the mapping: its reference count tells whether a result still
+        # lives on this generation
+        self._raw = np.frombuffer(self._map, dtype=np.uint8)
+        self.np_cols = self._raw[: 6 * 8 * n].view(np.float64).reshape(6, n)
+        self.np_succ = self._raw[6 * 8 * n: 6 * 8 * n + n]
+        self.cols = torch.from_numpy(self.np_cols)      # the D2H destinations
+        self.succ = torch.from_numpy(self.np_succ)
+        self._own_refs = sys.getrefcount(self._raw)
+        rc = torch.cuda.cudart().cudaHostRegister(self.cols.data_ptr(), size, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared summary block failed ({rc})")
+        self._registered = (self.cols.data_ptr(), size)
+
+    def is_free(self) -> bool:
+        """No numpy view of a previous result still references the block."""
+        import sys
+
+        return self.cols is not None and sys.getrefcount(self._raw) <= self._own_refs
+
+    def __del__(self):  # pragma: no cover
+        try:
+            import torch
+
+            if getattr(self, "_registered", None):
+                torch.cuda.cudart().cudaHostUnregister(self._registered[0])
+        except Exception:
+            pass

@@ -191,18 +191,20 @@ class DeviceAggregates:
             torch.cuda.current_stream().wait_event(self.ready)
 
     def to_host(self) -> Dict[str, Any]:
-        sim, args = getattr(self, "redo", (None, None))
+        """Copy the aggregates (a few KB) to the host. On several GPUs this is a COLLECTIVE call in
+        the rare case handled below (every rank must call it, as every rank must have called
+        aggregates_device): the flag it looks at is identical on all ranks."""
         if getattr(self, "ready", None) is not None:
             self.ready.synchronize()  # pipelined call: the reductions ran on their own stream
-        if sim is not None:
-            import torch
-
-            torch.cuda.current_stream().synchronize()
-            if not sim._selects_ok():  # multi-GPU only, rare: a select shortcut gave up on a row
-                with sim._stepwise_selects():
-                    again = sim.aggregates_device(**args)
-                again.redo = (None, None)
-                return again.to_host()
+        flag = getattr(self, "select_flag", None)
+        if flag is not None and int(flag.item()) != 0:
+            # multi-GPU only, rare: the pooled select could not finish a row from the pooled
+            # candidates. THIS aggregate's batch is still resident (self.batch owns the series), so
+            # the rows are selected again with the plain stepwise protocol — nothing is re-simulated.
+            sim, kw = self.reselect
+            sim.select_fallbacks += 1
+            again = sim._aggregate_batch(self.batch, stepwise=True, **kw)
+            return again.to_host()
         b = self.batch
         n, T, R = int(getattr(self, "n_override", b.n)), b.T, b.R
         nq, nw, nf = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES), len(FINAL_BALANCE_QUANTILES)
@@ -286,6 +288,7 @@ class RetirementMonteCarloSimulator:
         if self.search_policy not in ("auto", "waves", "probe", "grid", "sequential"):
             raise ValueError("search_policy must be 'auto', 'waves', 'probe', 'grid' or 'sequential'")
         self._device_index = device
+        self.select_fallbacks = 0  # several GPUs: selects repeated with the stepwise protocol (see DeviceAggregates.to_host)
         self._ctx: Optional[native.Context] = None
         self.last_search_stats: Dict[str, Any] = {}
         logger.info(f"Simulator initialized for scenario '{p.Nickname}' with main seed: {self.main_seed}")
@@ -517,21 +520,15 @@ class RetirementMonteCarloSimulator:
         plan.append(tuple(cur))
         return plan
 
-    def _selects_ok(self) -> bool:
-        """Hook, called at a host sync point: did every deferred select since the last call finish?"""
-        return True
-
-    def _stepwise_selects(self):
-        """Hook: context in which selects avoid any shortcut that _selects_ok() could reject."""
-        import contextlib
-
-        return contextlib.nullcontext()
-
-    def _select(self, specs, out16, counts=None) -> None:
-        """Hook: all select rows of a step in one launch sequence (ShardedSimulator adds the all-reduce)."""
+    def _select(self, specs, out16, counts=None, stepwise: bool = False):
+        """Hook: all select rows of a step in one launch sequence. Returns None, or (several GPUs,
+        ShardedSimulator) a 1-element device tensor that is non-zero when the pooled shortcut could
+        not finish some row — identical on every rank; the caller then selects again with
+        `stepwise=True` while the rows are still resident."""
         self.native_context.quantiles_rows(specs, out16, counts=counts)
+        return None
 
-    def _band_quantiles(self, b: DeviceBatch, bands, real_bands, wr_bands, wr_counts) -> None:
+    def _band_quantiles(self, b: DeviceBatch, bands, real_bands, wr_bands, wr_counts, stepwise: bool = False):
         """7-quantile nominal / real bands and 5-quantile NaN-skipping withdrawal-rate bands
         (simulation.py:1045-1118) of a batch, as ONE multi-row select."""
         import torch
@@ -543,11 +540,12 @@ class RetirementMonteCarloSimulator:
                  + ctx.series_rows(b.wr, n, R, WITHDRAWAL_RATE_QUANTILES))
         out16 = torch.empty((2 * T + R, 16), dtype=torch.float64, device=b.cols.device)
         cnt = torch.empty(2 * T + R, dtype=torch.int64, device=b.cols.device)
-        self._select(specs, out16, cnt)
+        flag = self._select(specs, out16, cnt, stepwise=stepwise)
         bands.view(T, nq).copy_(out16[:T, :nq])
         real_bands.view(T, nq).copy_(out16[T:2 * T, :nq])
         wr_bands.view(R, nw).copy_(out16[2 * T:, :nw])
         wr_counts.copy_(cnt[2 * T:])
+        return flag
 
     def _sample_columns(self, n: int) -> List[int]:
         """Columns DataFrame.sample(n=5, axis=1, random_state=main_seed) picks
@@ -697,12 +695,13 @@ class RetirementMonteCarloSimulator:
                 if t is not None:
                     t.record_stream(side)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            agg = self._aggregate_batch(b, n_global, offset, working_months, bands, plan, samples, part_first)
+            kw = dict(n_global=n_global, offset=offset, working_months=working_months, bands=bands, plan=plan,
+                      samples=samples, part_first=part_first)
+            agg = self._aggregate_batch(b, **kw)
             if side is not None:
                 agg.ready = torch.cuda.Event()
                 agg.ready.record(side)
-        agg.redo = (self, dict(working_months=working_months, num_simulations=num_simulations, bands=bands,
-                               first_path=first_path, samples=samples))
+        agg.reselect = (self, kw)
         return agg
 
     def _reduction_stream(self):
@@ -713,13 +712,17 @@ class RetirementMonteCarloSimulator:
         return self._side_stream
 
     def _aggregate_batch(self, b: DeviceBatch, n_global: int, offset: int, working_months: int, bands: bool,
-                         plan: List[Tuple[str, ...]], samples: bool, part_first: int) -> "DeviceAggregates":
-        """Every reduction of aggregates_device over one resident batch, on the current stream."""
+                         plan: List[Tuple[str, ...]], samples: bool, part_first: int,
+                         stepwise: bool = False) -> "DeviceAggregates":
+        """Every reduction of aggregates_device over one resident batch, on the current stream.
+        `stepwise`: the re-select of DeviceAggregates.to_host() (several GPUs, rare) — the counters
+        of `b` are global already and the pooled shortcut of the select is not taken."""
         import torch
 
         ctx = self.native_context
         n = b.n
-        self._reduce_counts(b.counters)
+        if not stepwise:
+            self._reduce_counts(b.counters)
         dev = b.cols.device
         T, R = b.T, b.R
         f64 = dict(dtype=torch.float64, device=dev)
@@ -740,7 +743,7 @@ class RetirementMonteCarloSimulator:
         desc = ctx.select_rows(specs)  # one descriptor per row (4 + 2T + R of them with the bands)
         out16 = torch.empty((len(desc), 16), **f64)
         cnt_all = torch.empty(len(desc), dtype=torch.int64, device=dev)
-        self._select(desc, out16, cnt_all)
+        flag = self._select(desc, out16, cnt_all, stepwise=stepwise)
         small[0:3].copy_(out16[0:3, 0])
         cnt.copy_(cnt_all[0:3])
         small[3:3 + nf].copy_(out16[3, :nf])
@@ -777,7 +780,14 @@ class RetirementMonteCarloSimulator:
                         n_rows += rows
                     o16 = torch.empty((n_rows, 16), **f64)
                     c16 = torch.empty(n_rows, dtype=torch.int64, device=dev)
-                    self._select(ctx.select_rows(specs_g), o16, c16)
+                    desc_g = ctx.select_rows(specs_g)
+                    flag_g = self._select(desc_g, o16, c16, stepwise=stepwise)
+                    # these series are released before the next pass, so a select that could not
+                    # finish is repeated NOW, while they are resident (the host sync below is needed
+                    # anyway); the flag is identical on every rank
+                    if flag_g is not None and int(flag_g.item()) != 0:
+                        self.select_fallbacks += 1
+                        self._select(desc_g, o16, c16, stepwise=True)
                     at = 0
                     for which in group:
                         rows, qs, off = layout[which]
@@ -798,6 +808,7 @@ class RetirementMonteCarloSimulator:
         agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
                                wr_counts=wr_counts, rates=rates, sample_block=sample_block)
         agg.n_override = n_global
+        agg.select_flag = flag
         return agg
 
     def _final_balance_histograms(self, b: DeviceBatch, rng_m, rng_1, hists) -> None:

@@ -42,7 +42,7 @@ def _path_succeeds(i: np.ndarray, wm: int) -> np.ndarray:
     return wm >= thr
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir):  # noqa: C901
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -91,16 +91,31 @@ def _worker(rank, world, port, out_dir):
         assert plan == [("traj",), ("real",), ("wr",)]                      # 70 % of the SMALLER 100 GB holds one series
         assert sim._series_plan(1_000_000, 61, 40, True, key=("c3",)) == [("traj", "real", "wr")]
         assert sim._series_plan(n, T, R, False, key=("none",)) == [()]
-        # deferred check of the pooled select: a non-zero "could not finish" count rejects the step once
-        assert sim._selects_ok()
-        sim._select_flag = torch.tensor([0])
-        assert sim._selects_ok() and sim._select_flag is None
-        sim._select_flag = torch.tensor([2])
-        assert not sim._selects_ok() and sim._selects_ok()
-        assert sim.select_fallbacks == 1
-        with sim._stepwise_selects():
-            assert sim._stepwise_only
-        assert not sim._stepwise_only
+        # the shared summary block of the sharded 7-tuple path (host side only here): rank 0 creates the
+        # POSIX shared-memory generation, rank 1 maps the same pages; a generation is busy while a
+        # numpy view of it (rank 0's DataFrame columns) is alive
+        import monte_carlo_retirement_b200.parallel as par
+
+        class _NoCudart:
+            def cudaHostRegister(self, *a):
+                return 0
+
+            def cudaHostUnregister(self, *a):
+                return 0
+
+        torch.cuda.cudart = lambda: _NoCudart()
+        blk = par._SharedSummaryBlock(coll, f"mcr_test_{port}", 0, 1000)
+        lo, cnt = shard_range(1000, rank, world)
+        blk.np_cols[:, lo:lo + cnt] = rank + 1.0
+        blk.np_succ[lo:lo + cnt] = rank + 1
+        coll.barrier()
+        assert blk.np_cols[3, 0] == 1.0 and blk.np_cols[3, 999] == 2.0 and blk.np_succ[499] == 1 and blk.np_succ[500] == 2
+        assert blk.is_free()
+        view = blk.np_cols[2]
+        assert not blk.is_free()
+        del view
+        assert blk.is_free()
+        coll.barrier()
         torch.save({"months": months, "prob": prob, "curve": curve, "events": events, "plan": plan},
                    os.path.join(out_dir, f"rank{rank}.pt"))
     finally:

@@ -37,8 +37,20 @@ def main():
             assert np.array_equal(va.to_numpy(), vb.to_numpy(), equal_nan=True), k
         else:
             assert va == vb or (va != va and vb != vb), (k, va, vb)
+    from monte_carlo_retirement_b200.parallel import shard_range
+
     ta, tb = sh.run_monte_carlo_simulations(wm, n), one.run_monte_carlo_simulations(wm, n)
-    assert ta[0].equals(tb[0])
+    lo, cnt = shard_range(n, dist.get_rank(), dist.get_world_size())
+    # summary_df: all rows on rank 0 (a view of the shared host block), the own shard elsewhere
+    want0 = tb[0] if dist.get_rank() == 0 else tb[0].iloc[lo:lo + cnt].reset_index(drop=True)
+    assert ta[0].equals(want0)
+    # a second call while the first result is alive must not overwrite it (block generations)
+    keep = ta[0].copy(deep=True)
+    t2 = sh.run_monte_carlo_simulations(wm + 12, n)
+    assert ta[0].equals(keep) and not t2[0].equals(keep)
+    del t2
+    t3 = sh.run_monte_carlo_simulations(wm, n)      # the freed generation is reused
+    assert t3[0].equals(keep) and len(sh._shared_blocks) == 2
     for i in (1, 3, 4):
         assert np.array_equal(ta[i].to_numpy(), tb[i].to_numpy(), equal_nan=True), i
     assert ta[2] == tb[2] and ta[5] == tb[5] and ta[6] == tb[6]
