@@ -19,10 +19,19 @@ final-balance quantiles and histograms, 7-quantile nominal/real bands, 5-quantil
 `e2e`     = the same metric through the reference-facing call
             RetirementMonteCarloSimulator.run_monte_carlo_simulations(240, 1_000_000) returning
             the reference's 7-tuple on the HOST (summary_df + band frames), wall-clocked.
-`roofline`= FP64-pipe issue slots: SURVEY §8d's W = 220 slots per executed path-month x executed
-            path-months of one launch / CUDA-event duration of the timeline kernel, against the
-            DFMA-chain peak measured in this run (the path is FP64-pipe bound, not HBM- or
-            tensor-bound; the HBM side is reported next to it).
+`roofline`= the timeline kernel against the unit that binds it. Measured (ncu + the issue-model
+            microbenchmarks in tools/microbench, profiles/r02_issue_model*.log): not HBM (2 %), not
+            the FP64 pipe (~50 % busy) but warp-instruction ISSUE — one instruction per clock per
+            SM sub-partition, of which the integer / FP32 work of the draws and selects (half-rate
+            on B200) takes most. `frac` = executed thread-instructions per second / (SMs x 4 x 32
+            x clock); the instruction count per path-month comes from an ncu capture of THIS build
+            (profiles/timeline_counts.json, keyed by a hash of the kernel sources — stale counts
+            are refused), the duration is CUDA events of this run. The FP64-pipe view, the
+            reference-order census W = 220 and the HBM side are reported next to it.
+`search`  = BASELINE.json configs[3]: find_minimum_working_months at 1e6 paths per candidate
+            (wall time; the full 601-candidate grid in one launch sequence; the selected month
+            checked against the reference's decision procedure on the same table).
+`c5`      = BASELINE.json configs[4] (8 GPUs only): 1e9 paths with bands + histograms, wall time.
 """
 from __future__ import annotations
 
@@ -212,31 +221,161 @@ def cpu_port_throughput(n_paths: int, procs: int):
     return n_paths * n_rows / dt, dt, ok / n_paths
 
 
+def _reference_worker(q, cfg_dict, wm, n, procs):
+    """Child process: the UNMODIFIED reference (oracle/_ref/backend) on the host cores."""
+    from oracle import ref as oracle_ref
+
+    sys.path.insert(0, oracle_ref.backend_path())
+    try:
+        from loguru import logger
+
+        logger.remove()
+    except Exception:
+        pass
+    import config as ref_config
+    import simulation as ref_simulation
+
+    cfg = ref_config.Config(**dict(cfg_dict, num_processes=procs))
+    sim = ref_simulation.RetirementMonteCarloSimulator(cfg)
+    sim.use_final_seeds()
+    t0 = time.perf_counter()
+    out = sim.run_monte_carlo_simulations(working_months=wm, num_simulations=n)
+    dt = time.perf_counter() - t0
+    q.put((dt, float(sim._success_probability(out[0]))))
+
+
+def reference_throughput(n_paths: int, procs: int):
+    """RetirementMonteCarloSimulator.run_monte_carlo_simulations of the real reference
+    (backend/simulation.py:952-1128, its own multiprocessing.Pool, :996-1001), in a fresh process
+    so that neither its flat module names nor its Pool touch this one. None when oracle/_ref is
+    not staged."""
+    import multiprocessing as mp
+
+    from oracle import ref as oracle_ref
+
+    if not oracle_ref.build():
+        return None
+    cfg = _scenario()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_reference_worker, args=(q, cfg, WORKING_MONTHS, n_paths, procs))
+    p.start()
+    dt, p_ok = q.get(timeout=1800)
+    p.join()
+    n_rows = WORKING_MONTHS + 12 * cfg["retirement_years"]
+    return n_paths * n_rows / dt, dt, p_ok
+
+
+REF_SAMPLE = 4000      # paths per step of the real (CPython) reference: ~1e5 path-months/s/core
+PORT_SAMPLE = 100_000  # paths per step of the C port
+
+
+def cpu_baseline_block(threads: int):
+    """cpu_baseline of the bench line: the real reference when oracle/_ref is staged (kind
+    "reference"), with the oracle port (same algorithm in C, the reference's numpy draws) beside
+    it; the port alone otherwise."""
+    port_v, port_dt, p_ok = cpu_port_throughput(PORT_SAMPLE, threads)
+    port = {"value": port_v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{PORT_SAMPLE} paths x 720 months of the same workload in {port_dt:.1f} s wall (numpy "
+                      f"SeedSequence/PCG64 draws + C port of the path engine, {threads} processes)",
+            "success_probability": p_ok * 100.0}
+    ref = reference_throughput(REF_SAMPLE, threads)
+    if ref is None:
+        return port
+    v, dt, p_ref = ref
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{REF_SAMPLE} paths x 720 months of the same workload in {dt:.1f} s wall: the unmodified "
+                      f"backend/simulation.py run_monte_carlo_simulations (oracle/_ref) with num_processes={threads}",
+            "success_probability": p_ref, "port": port}
+
+
+CPU_SEARCH_N = 1000  # paths per probe of the CPU arm's sequential search (the GPU arm uses 1e6)
+
+
+def _reference_search_worker(q, cfg_dict, procs):
+    from oracle import ref as oracle_ref
+
+    sys.path.insert(0, oracle_ref.backend_path())
+    try:
+        from loguru import logger
+
+        logger.remove()
+    except Exception:
+        pass
+    import config as ref_config
+    import simulation as ref_simulation
+
+    sim = ref_simulation.RetirementMonteCarloSimulator(ref_config.Config(**dict(cfg_dict, num_processes=procs)))
+    t0 = time.perf_counter()
+    months, prob, curve = sim.find_minimum_working_months(verbose=False)
+    q.put((time.perf_counter() - t0, months, prob, len(curve)))
+
+
+def cpu_search_block(threads: int):
+    """BASELINE.json configs[3] on the host cores: the reference's SEQUENTIAL search
+    (backend/simulation.py:1138-1342, one run_monte_carlo_simulations per probe) on config.json at
+    CPU_SEARCH_N paths per probe; linear in the paths per probe, so the 1e6-path figure is an
+    extrapolation and says so."""
+    import multiprocessing as mp
+
+    import scenarios
+    from oracle import ref as oracle_ref
+
+    cfg = dict(scenarios.CONFIG_JSON, num_simulations_search=CPU_SEARCH_N)
+    if oracle_ref.build():
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_reference_search_worker, args=(q, cfg, threads))
+        p.start()
+        dt, months, prob, probes = q.get(timeout=1800)
+        p.join()
+        kind = "reference"
+    else:
+        from oracle import oracle as orc
+
+        orc.build()
+        sim = orc.OracleSimulator(cfg, n_threads=threads)
+        t0 = time.perf_counter()
+        months, prob, curve, _ = sim.find_minimum_working_months()
+        dt, probes, kind = time.perf_counter() - t0, len(curve), "port"
+    return {"kind": kind, "cores": threads, "paths_per_probe": CPU_SEARCH_N, "probes": probes, "wall_s": dt,
+            "selected_working_months": months, "probability": prob,
+            "extrapolated_wall_s_at_1e6_paths_per_probe": dt * 1_000_000 / CPU_SEARCH_N}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    sample = 100_000
+    from oracle import ref as oracle_ref
+
+    real = oracle_ref.build()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, _ = cpu_port_throughput(sample, threads)
+        if real:
+            v, dt, _ = reference_throughput(REF_SAMPLE, threads)
+        else:
+            v, dt, _ = cpu_port_throughput(PORT_SAMPLE, threads)
         if i >= args.warmup:
             vals.append((v, dt))
     value = statistics.mean(v for v, _ in vals)
     ms = statistics.mean(dt for _, dt in vals) * 1e3
+    sample = REF_SAMPLE if real else PORT_SAMPLE
+    what = ("the unmodified reference (oracle/_ref/backend/simulation.py, run_monte_carlo_simulations with "
+            f"num_processes={threads})" if real else
+            "C port of backend/simulation.py (oracle/path_oracle.c) + the reference's numpy draws; oracle/_ref not staged")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} paths x 720 months per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} paths x 720 months per step (numpy PCG64 draws + C path engine, "
-                                   f"{threads} processes)"},
+        "config": {"workload": WORKLOAD + f"; CPU arm: a {sample}-path sample of it per step (linear in paths)",
+                   "sample": f"{sample} paths x 720 months per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference" if real else "port",
+                         "sample": f"{sample} paths x 720 months per step ({what})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "C port of backend/simulation.py (oracle/path_oracle.c) + the reference's numpy draws; the "
-                "unmodified CPython reference measured 1.09e5 path-months/s/core in the build container",
+        "note": what,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -256,18 +395,12 @@ def run_b200_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cpu_line = None
+    cpu_line = cpu_search = None
     if world == 1 and not args.no_cpu_baseline:
-        # before CUDA is initialised in this process (the CPU arm forks workers)
+        # before CUDA is initialised in this process (the CPU arms fork / spawn workers)
         threads = os.cpu_count() or 1
-        sample = 100_000
-        v, dt, p_ok = cpu_port_throughput(sample, threads)
-        cpu_line = {
-            "value": v, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample} paths x 720 months of the same workload in {dt:.1f} s wall (numpy SeedSequence/PCG64 "
-                      f"draws + C port of the path engine, {threads} processes); the unmodified CPython reference "
-                      "measured 1.09e5 path-months/s/core in the build container (BASELINE.md)",
-            "success_probability": p_ok * 100.0}
+        cpu_line = cpu_baseline_block(threads)
+        cpu_search = cpu_search_block(threads)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -365,7 +498,14 @@ def run_b200_arm(args):
     h2d = 1024  # scenario constants + launch arguments (kernel parameter blocks); there is no bulk input
     d2h = int(getattr(sim, "last_d2h_bytes", n_job * 45))
 
+    # ---- BASELINE.json configs[3]: the search at 1e6 paths per candidate (outside the timed C3 region)
+    search = search_block(world, local_rank) if not args.no_search else None
+    # ---- BASELINE.json configs[4]: 1e9 paths over the 8 GPUs of the box
+    c5 = c5_block(world, local_rank) if (world >= 8 and not args.no_c5) else None
+
     if rank == 0:
+        from monte_carlo_retirement_b200.build import source_hash
+
         T = sim._trajectory_len(WORKING_MONTHS)
         alg_bytes = n * ((2 * T + R) * 8 + 5 * 8 + 1 + 4)  # series + summary columns written per launch
         peaks = {}
@@ -375,64 +515,167 @@ def run_b200_arm(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = executed * W_SLOTS_PER_PATH_MONTH / (kernel_ms * 1e-3)
         counts = {}
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_timeline_counts.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "timeline_counts.json")) as f:
                 counts = json.load(f)
         except Exception:
             pass
-        fp64_exec = counts.get("fp64_pipe_instructions_per_path_month")
-        executed_block = None
-        if fp64_exec:
-            executed_block = {
-                "fp64_instr_per_path_month": fp64_exec,
-                "all_instr_per_path_month": counts.get("warp_instructions_per_path_month"),
-                "fp64_slots_per_s": executed * fp64_exec / (kernel_ms * 1e-3),
-                "fp64_pipe_frac_of_peak": executed * fp64_exec / (kernel_ms * 1e-3) / fp64_peak,
-                "issue_slots_active_pct_ncu": counts.get("issue_slots_active_pct"),
-                "note": "the fast build's closed forms need fewer FP64 instructions than the reference-faithful census "
-                        "W=220; the kernel is issue-slot bound (ncu), not FP64-pipe bound",
-                "source": counts.get("source")}
+        fresh = bool(counts) and counts.get("source_hash") == source_hash()
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clock_hz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        issue_peak = sm_count * 4 * 32 * clock_hz        # thread-instructions / s: 1 warp-instruction / clk / SMSP
+        t_kernel = kernel_ms * 1e-3
+        roofline = {
+            "bound": "issue", "unit": "Tinst/s", "peak": issue_peak / 1e12,
+            "peak_source": f"{sm_count} SMs x 4 sub-partitions x 32 lanes x {clock_hz / 1e6:.0f} MHz (SM clock sampled in this run)",
+            "kernel": "k_timeline<fast, philox, bounded-return variant>", "kernel_ms": kernel_ms,
+            "kernel_share_of_step": kernel_ms / ms_per_step,
+            "executed_path_months_per_launch": executed,
+            "why": "ncu: warp-instruction issue is the busiest unit (~70 %), FP64 pipe ~50 %, XU ~36 %, HBM 3 %; "
+                   "tools/microbench/issue_model2.cu: integer multiplies / logic / selects issue at half rate on the "
+                   "datapath they share with FP32, so the draws and selects, not the FP64 arithmetic, set the pace",
+            "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / t_kernel / 1e9,
+                    "peak_gbs": hbm_peak, "frac": alg_bytes / t_kernel / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
+            # the reference-order census of SURVEY §8d, kept as a secondary figure: how many of the
+            # reference's own FP64 issue slots per second this kernel retires (the closed forms need
+            # far fewer FP64 instructions than the census, so this exceeds the FP64 peak)
+            "reference_order": {"W_slots_per_path_month": W_SLOTS_PER_PATH_MONTH,
+                                "slots_per_s": executed * W_SLOTS_PER_PATH_MONTH / t_kernel,
+                                "fp64_peak_slots_per_s": fp64_peak,
+                                "ratio_to_fp64_peak": executed * W_SLOTS_PER_PATH_MONTH / t_kernel / fp64_peak,
+                                "peak_source": "DFMA-chain microbenchmark measured in this run (mcr_fp64_peak_slots_per_s)"},
+        }
+        if fresh:
+            ipm, fpm = counts["instr_per_path_month"], counts["fp64_instr_per_path_month"]
+            achieved = executed * ipm / t_kernel
+            roofline.update({
+                "achieved": achieved / 1e12, "frac": achieved / issue_peak,
+                "traffic": counts["ncu"]["dram_bytes_read"] + counts["ncu"]["dram_bytes_write"],
+                "issue": {"instr_per_path_month": ipm, "non_fp64_instr_per_path_month": ipm - fpm,
+                          "issue_peak_tinst_s": issue_peak / 1e12, "frac": achieved / issue_peak,
+                          "ncu_issue_active_pct": counts["ncu"]["issue_active_pct"]},
+                "fp64_pipe": {"fp64_instr_per_path_month": fpm, "slots_per_s": executed * fpm / t_kernel,
+                              "peak_slots_per_s": fp64_peak, "frac": executed * fpm / t_kernel / fp64_peak,
+                              "ncu_fp64_pipe_active_pct": counts["ncu"]["fp64_pipe_active_pct"]},
+                "counts_source": counts.get("source"), "counts_source_hash": counts.get("source_hash"),
+            })
+        else:
+            roofline.update({"achieved": None, "frac": None, "traffic": None,
+                             "stale_counts": "profiles/timeline_counts.json was taken from another build of the kernel "
+                                             f"(hash {counts.get('source_hash')} != {source_hash()}); re-run "
+                                             "tools/make_timeline_counts.py on an ncu capture of this build"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "paths_per_gpu": n, "months": months,
+            "config": {"workload": WORKLOAD + (f"; cpu_baseline: a {REF_SAMPLE}-path sample of it (real reference) / "
+                                               f"{PORT_SAMPLE}-path sample (C port), linear in paths"
+                                               if cpu_line is not None else ""),
+                       "paths_per_gpu": n, "months": months,
                        "l2": "no HBM inputs (counter-based Philox); each step writes 1.36 GB of outputs, > 126 MB L2",
                        "success_probability": host["success_probability"],
-                       # N > 1: times the pooled distributed select gave up on a row and the step was
-                       # re-run with the stepwise protocol (checked after the timed loop; 0 = the timed
-                       # steps are the whole work)
+                       # N > 1: selects repeated with the stepwise protocol because the pooled shortcut
+                       # could not finish a row (0 = the timed steps are the whole work)
                        "select_fallbacks": int(getattr(sim, "select_fallbacks", 0)),
+                       "parity": "this kernel variant (bounded-return specialisation, lean month steps, MUFU normals) "
+                                 "passes the <= 1e-9 / bit-exact-flags replay gate on the reference's numpy draws "
+                                 "(tests/test_gpu_parity.py::test_benchmarked_variant_meets_the_replay_gate); its own "
+                                 "Philox draws are statistically, not path-wise, comparable to numpy's",
                        "pipeline": bool(args.pipeline)},
-            "roofline": {
-                "bound": "fp64_pipe", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "Tslot/s",
-                "frac": achieved / fp64_peak,
-                "traffic": (counts.get("dram_bytes_read", 0) + counts.get("dram_bytes_write", 0)) or None,
-                "executed": executed_block,
-                "kernel": "k_timeline<fast,philox>", "kernel_ms": kernel_ms,
-                "kernel_share_of_step": kernel_ms / ms_per_step,
-                "algorithmic_slots_per_path_month": W_SLOTS_PER_PATH_MONTH,
-                "executed_path_months_per_launch": executed,
-                "peak_source": "DFMA-chain microbenchmark measured in this run (burst, mcr_fp64_peak_slots_per_s)",
-                "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
-                        "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                        "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"},
-            },
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(e2e_t[0]) * 1e3,
-                    "api": f"RetirementMonteCarloSimulator.run_monte_carlo_simulations(240, {n_job}) -> host 7-tuple"},
+                    "api": f"RetirementMonteCarloSimulator.run_monte_carlo_simulations(240, {n_job}) -> host 7-tuple"
+                           + ("; summary_df: all rows on rank 0 (shared pinned host block), own shard elsewhere"
+                              if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
+        if search is not None:
+            if cpu_search is not None:
+                search["cpu"] = cpu_search
+            line["search"] = search
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _sim_for(cfg_dict, world, local_rank, **kw):
+    from monte_carlo_retirement_b200.config import Config
+    from monte_carlo_retirement_b200.simulation import RetirementMonteCarloSimulator
+
+    cfg = Config(**cfg_dict)
+    if world > 1:
+        from monte_carlo_retirement_b200.parallel import ShardedSimulator
+
+        return ShardedSimulator(cfg, device=local_rank, **kw)
+    return RetirementMonteCarloSimulator(cfg, device=local_rank, **kw)
+
+
+def search_block(world: int, local_rank: int):
+    """configs[3]: config.json, 1e6 paths per candidate (global, sharded over the ranks).
+    `auto`: the shipped policy (one search launch per probe at this size); `grid`: every month
+    start..start+600 in ONE launch, the reference's decisions replayed over the table. Both read
+    the same common-random-number table, so they must select the same month."""
+    import torch
+
+    import scenarios
+
+    cfg = dict(scenarios.CONFIG_JSON, num_simulations_search=1_000_000)
+    out = {"workload": "config.json, 1e6 paths per candidate, candidates 0..600 (grid) / the reference's probes (auto)",
+           "n_gpus": world}
+    results = {}
+    for policy in ("auto", "grid"):
+        sim = _sim_for(cfg, world, local_rank, search_policy=policy)
+        sim.native_context  # noqa: B018  context creation is not part of the search
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        months, prob, curve = sim.find_minimum_working_months(verbose=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        results[policy] = (months, prob)
+        out[policy] = {"wall_s": dt, "selected_working_months": months, "probability": prob, "probes": len(curve),
+                       "launches": sim.last_search_stats.get("launches"),
+                       "candidates_evaluated": sim.last_search_stats.get("candidates_evaluated")}
+    out["policies_agree"] = results["auto"] == results["grid"]
+    return out
+
+
+def c5_block(world: int, local_rank: int):
+    """configs[4]: 1e9 paths of config.json at working_months = 233 over all ranks, nominal / real /
+    withdrawal-rate bands, histograms and summary statistics; aggregate-only (nothing N-sized
+    leaves the GPUs). Wall time of the second call (the first also pays the cudaMalloc of the
+    series blocks)."""
+    import torch
+    import torch.distributed as dist
+
+    import scenarios
+
+    sim = _sim_for(dict(scenarios.CONFIG_JSON), world, local_rank)
+    sim.use_final_seeds()
+    n, wm = 1_000_000_000, 233
+    walls = []
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        agg = sim.run_aggregates(wm, n, bands=True)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    months = wm + 12 * sim.params_model.retirement_years
+    return {"workload": "config.json, 1e9 paths, wm=233, bands + histograms, aggregate-only", "n_gpus": world,
+            "wall_s": walls[-1], "wall_s_each_call": walls, "nominal_path_months_per_s": n * months / walls[-1],
+            "executed_path_months": agg["executed_path_months"], "success_probability": agg["success_probability"],
+            "series_passes": [list(g) for g in sim.last_series_plan],
+            "select_fallbacks": int(getattr(sim, "select_fallbacks", 0))}
 
 
 def main():
@@ -442,6 +685,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-search", action="store_true", help="skip the configs[3] search block")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] 1e9-path block (8 GPUs)")
     ap.add_argument("--pipeline", type=int, default=0, choices=[0, 1],
                     help="1: reductions of step i on a second stream, under the timeline kernel of step i+1")
     args = ap.parse_args()

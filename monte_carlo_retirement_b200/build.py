@@ -50,6 +50,22 @@ def _sources_mtime() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
+def source_hash() -> str:
+    """sha256 over the sources of the timeline kernel (everything mcr_kernels_fast.cu includes) and
+    the tuning macros — the identity of the built kernel. profiles/timeline_counts.json (ncu
+    instruction counts) is keyed by it, so bench.py never quotes counts taken from another build."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in ("mcr_kernels_fast.cu", "mcr_kernels.cuh", "mcr_path.cuh", "mcr_rng.cuh", "mcr_portable.h",
+              "mcr_derive.h", "mcr_internal.h"):
+        h.update(f.encode())
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    h.update(f"{os.environ.get('MCR_MIN_BLOCKS', '')}|{os.environ.get('MCR_BLOCK', '')}".encode())
+    return h.hexdigest()[:16]
+
+
 def needs_build() -> bool:
     return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _sources_mtime()
 

@@ -507,6 +507,7 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
 int64_t mcr_select_state_bytes(int32_t rows) { return (int64_t)quantile_state_bytes(rows); }
 int64_t mcr_select_hist_bytes(int32_t rows) { return (int64_t)quantile_hist_bytes(rows); }
 int32_t mcr_select_full_passes(void) { return select_full_passes(); }
+int32_t mcr_select_full_passes_for(int64_t n_global_max) { return select_full_passes_for(n_global_max); }
 int64_t mcr_select_exchange_words(int32_t rows, int32_t world) { return (int64_t)select_exchange_words(rows, world); }
 void mcr_select_exchange_layout(int32_t rows, int32_t world, int64_t* at4) {
   if (at4) select_exchange_layout(rows > 0 ? rows : 1, world > 0 ? world : 1, at4);
@@ -518,6 +519,8 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
   std::lock_guard<std::mutex> lk(ctx->mu);
   const bool pooled_step = step >= MCR_SELECT_POOL_EXPORT && step <= MCR_SELECT_POOL_TAIL;
   const int rank = pass & 0xff, world = (pass >> 8) & 0xff;  // POOL_* steps: pass = rank | world << 8
+  const int sampled = (step == MCR_SELECT_HIST) ? (pass >> 8) & 1 : 0;   // HIST: MCR_SELECT_HIST_SAMPLED
+  if (step == MCR_SELECT_HIST) pass &= 0xff;
   if (pooled_step ? (world < 1 || rank >= world) : (pass < 0 || pass > 15)) return fail(ctx, MCR_EINVAL, "bad pass");
   std::vector<RowDesc> d;
   if (int rc = make_descs(ctx, rows_host, n_rows, d)) return rc;
@@ -541,7 +544,7 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
       MCR_CUDA(ctx, launch_sel_extremes(n_rows, state_dev, (long long*)out_dev, step == MCR_SELECT_EXTREMES_SET, st));
       break;
     case MCR_SELECT_HIST:
-      MCR_CUDA(ctx, launch_sel_hist(n_rows, max_n, pass, state_dev, hist_dev, st));
+      MCR_CUDA(ctx, launch_sel_hist(n_rows, max_n, pass, state_dev, hist_dev, st, sampled));
       break;
     case MCR_SELECT_COLLECT:
       MCR_CUDA(ctx, launch_sel_collect(n_rows, max_n, state_dev, st));

@@ -70,7 +70,9 @@ struct SelRow {
   int32_t gbig[kMaxTargets];        // per group: bucket too large for the candidate list (not gathered)
   int32_t group[kMaxTargets];       // target -> group
   int32_t slot[kMaxTargets];        // (quantile, lo/hi) -> rank-sorted target slot
-  uint64_t kmin, kmax;              // row extremes (pass 0, adaptive mode)
+  uint64_t kmin, kmax;              // row extremes over the keys != +0.0 (pass 0, adaptive mode)
+  uint32_t fixed_mask;              // targets resolved to +0.0 by the first digit pass (see advance_row)
+  uint32_t pad0;
   int64_t n_valid;
   int32_t n_groups;
   int32_t rb;                       // resolved bits (64 == done)
@@ -83,15 +85,27 @@ struct SelRow {
 };
 
 constexpr int kHistThreads = 256;
-constexpr int kChunk = 16384;       // elements of one row handled by one CTA
+constexpr int kChunk = 16384;       // elements of one row handled by one CTA (short rows; long rows: chunk_for)
+constexpr int kMaxChunksPerRow = 1024;  // a long row is cut into at most this many chunks: fewer CTAs merging their
+                                        // shared histograms into the row's global one (1.25e8-element rows: 7630 -> 954)
 constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
 constexpr int kBigBucket = 2048;    // buckets above this are not gathered (resolved by min == max, else by scanning)
-constexpr int kFullPasses = 4;      // passes that may scan the rows before the collect (pass 0 + up to 3 digits)
+constexpr int kFullPasses = 4;      // passes that may scan the rows before the collect (pass 0 + up to 3 digits);
+constexpr int kFullPassesLong = 5;  // one more digit for rows of more than 2^27 elements (GLOBAL length)
+constexpr int64_t kLongRow = (int64_t)1 << 27;
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 constexpr int kSampleStride = 16;   // adaptive pass 0 reads every 16th chunk of a long row ...
 constexpr int kSampleMinChunks = 8; // ... rows of up to 8 chunks are read whole
 constexpr int kMaxCommonBits = 56;  // the first digit pass always has a digit left to count with
 constexpr int kBelowAt = 256, kAboveAt = 257;  // H slots of the keys outside the sampled prefix (first digit pass)
+constexpr int kBelowOtherAt = 258;             // ... and of the keys below it that are not +0.0
+// The engine pads the yearly series of a failed path with +0.0 (simulation.py:905-912) and clamps final
+// balances at 0, so rows hold a mass of exact zeros next to a bulk of positive balances. Zeros share
+// only the sign bit with the bulk: a common prefix over all keys would be worthless and the zero
+// bucket never shrinks. The adaptive start therefore takes the row extremes over the keys != +0.0,
+// the first digit pass counts the zeros as `below`, and a target whose rank falls into a `below`
+// mass made of zeros only IS +0.0 — resolved on the spot.
+constexpr uint64_t kZeroKey = 0x8000000000000000ull;
 
 __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, const RowDesc* __restrict__ desc,
                            int adaptive, int fused) {
@@ -101,7 +115,7 @@ __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ his
   for (int k = threadIdx.x; k < kHistWords; k += blockDim.x) H[k] = 0;
   if (threadIdx.x == 0) {
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
-    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused; R.ready = 0;
+    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused; R.ready = 0; R.fixed_mask = 0;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
@@ -276,7 +290,7 @@ __device__ __forceinline__ void extremes_elements(const double* __restrict__ x, 
   uint64_t lo_k = ~0ull, hi_k = 0ull;
   scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
     const uint64_t k = ((uint64_t)hi << 32) | lo;
-    if (ok) {
+    if (ok && k != kZeroKey) {
       lo_k = k < lo_k ? k : lo_k;
       hi_k = k > hi_k ? k : hi_k;
     }
@@ -309,6 +323,7 @@ __device__ __forceinline__ void first_digit_elements(const Probe& P, const doubl
       } else {  // first differing bit decides the side: the key has a 1 where the prefix has a 0 <=> above
         const uint64_t kp = k & (((uint64_t)P.m_hi << 32) | P.m_lo), pp = ((uint64_t)P.p_hi << 32) | P.p_lo;
         id = kp > pp ? kAboveAt : kBelowAt;
+        if (id == kBelowAt && k != kZeroKey) red_shared_add(P.a_hist + (uint32_t)kBelowOtherAt * 4u, 1u);  // (rare)
       }
     }
     const int id0 = __shfl_sync(0xffffffffu, id, 0);
@@ -323,8 +338,11 @@ __device__ __forceinline__ void first_digit_elements(const Probe& P, const doubl
 // One pass, first half: histogram of the next digit inside every live prefix bucket. Rows that
 // are finished or ready for the collect skip; rows with a valid candidate list scan that list
 // (one CTA).
+// chunk: elements per CTA (a multiple of 4 * kHistThreads); stride: pass 0 of an adaptive call
+// launches one CTA per `stride` chunks (the sample), every other pass has stride 1.
 __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
-                                                           const double* __restrict__ cand, int pass) {
+                                                           const double* __restrict__ cand, int pass, int chunk,
+                                                           int stride) {
   extern __shared__ uint32_t sh[];  // [n_groups][256]
   __shared__ PrefixTable T;
   SelRow& R = rows[blockIdx.y];
@@ -333,23 +351,29 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
   const bool from_cand = R.collected && !R.overflow;
   if (from_cand && blockIdx.x > 0) return;
   const int64_t n = R.d.n;
-  if (!from_cand && (int64_t)blockIdx.x * kChunk >= n) return;
+  const bool sampling = pass == 0 && R.adaptive;
+  // pass 0 of an adaptive row: a long row is sampled, one 16 K-element piece out of `stride` (what the
+  // sample misses is handled exactly by the below / above counts of the next pass); rows of up to
+  // kSampleMinChunks pieces are read whole by their first CTAs
+  int64_t begin = (int64_t)blockIdx.x * chunk;
+  if (sampling) {
+    const int64_t pieces = (n + kChunk - 1) / kChunk;
+    begin = pieces > kSampleMinChunks ? (int64_t)blockIdx.x * stride * kChunk : (int64_t)blockIdx.x * kChunk;
+    chunk = kChunk;
+  }
+  if (from_cand) begin = 0;
+  if (!from_cand && begin >= n) return;
   uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
-  const int64_t begin = from_cand ? 0 : (int64_t)blockIdx.x * kChunk;
-  const int cnt = from_cand ? R.n_cand : (int)(begin + kChunk < n ? kChunk : n - begin);
+  const int cnt = from_cand ? R.n_cand : (int)(begin + chunk < n ? chunk : n - begin);
   const double* __restrict__ x = (from_cand ? cand + (size_t)blockIdx.y * kCandCap : R.d.x) + begin;
   const uint8_t* __restrict__ m = (from_cand || !R.d.mask) ? nullptr : R.d.mask + begin;
-  if (pass == 0 && R.adaptive) {
-    // a long row is sampled: every kSampleStride-th chunk (what the sample misses is handled
-    // exactly by the below / above counts of the next pass)
-    const int64_t chunks = (n + kChunk - 1) / kChunk;
-    if (chunks > kSampleMinChunks && (blockIdx.x % kSampleStride) != 0) return;
+  if (sampling) {
     if (m) extremes_elements<kHistThreads, true>(x, m, cnt, R); else extremes_elements<kHistThreads, false>(x, m, cnt, R);
     return;
   }
   const bool first_digit = pass == 1 && R.adaptive && rb > 0;  // counts keys outside the sampled prefix too
   const int ng = R.n_groups;
-  const int used = first_digit ? 2 * 256 : ng * 256;
+  const int used = first_digit ? 2 * 256 : ng * 256;   // (first digit: 256 bins + below / above / below-other)
   for (int k = threadIdx.x; k < used; k += kHistThreads) sh[k] = 0;
   if (rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
   const int w = 64 - rb < 8 ? 64 - rb : 8;
@@ -388,7 +412,8 @@ __device__ __forceinline__ void collect_elements(const Probe& P, const double* _
   });
 }
 
-__global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand) {
+__global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand,
+                                                              int chunk) {
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
   __shared__ int s_big[kMaxTargets];
@@ -396,15 +421,15 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
   const int rb = R.rb;
   if (rb >= 64 || R.collected) return;
   const int64_t n = R.d.n;
-  if ((int64_t)blockIdx.x * kChunk >= n) return;
+  if ((int64_t)blockIdx.x * chunk >= n) return;
   const int ng = R.n_groups;
   if (threadIdx.x < kMaxTargets) {
     s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull;
     s_big[threadIdx.x] = threadIdx.x < ng ? R.gbig[threadIdx.x] : 0;
   }
   if (rb > 0) build_table(T, R, ng, rb); else __syncthreads();
-  const int64_t begin = (int64_t)blockIdx.x * kChunk;
-  const int cnt = (int)(begin + kChunk < n ? kChunk : n - begin);
+  const int64_t begin = (int64_t)blockIdx.x * chunk;
+  const int cnt = (int)(begin + chunk < n ? chunk : n - begin);
   const double* __restrict__ x = R.d.x + begin;
   const uint8_t* __restrict__ m = R.d.mask ? R.d.mask + begin : nullptr;
   double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
@@ -527,28 +552,49 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
           const int64_t below = first_digit ? (int64_t)H[kBelowAt] : 0, above = first_digit ? (int64_t)H[kAboveAt] : 0;
+          const bool below_is_zeros = first_digit && H[kBelowOtherAt] == 0;
           set_target_ranks(R, part + below + above);
           if (!adaptive) {
             for (int t = 0; t < nt; ++t) { R.prefix[t] = 0; R.group[t] = 0; }
           } else {
-            // ranks inside the prefix bucket; a target outside it restarts the row
+            // ranks inside the prefix bucket. A target below it is +0.0 when the whole `below` mass is
+            // (zero-padded failures); any other target outside the bucket restarts the row.
+            uint32_t fixed = 0;
             for (int t = 0; t < nt; ++t) {
-              if (R.n_valid > 0 && (R.rank[t] < below || R.rank[t] >= below + part)) s_restart = 1;
+              if (R.n_valid > 0) {
+                if (R.rank[t] < below) {
+                  if (below_is_zeros) fixed |= 1u << t; else s_restart = 1;
+                } else if (R.rank[t] >= below + part) {
+                  s_restart = 1;
+                }
+              }
               R.rank[t] -= below;
             }
             if (s_restart) {
+              fixed = 0;
               for (int t = 0; t < nt; ++t) { R.rank[t] += below; R.prefix[t] = 0; R.group[t] = 0; R.bcount[t] = R.n_valid; }
+            } else if (fixed) {
+              // targets are rank-sorted, so the fixed ones come first: they shadow the first live
+              // target from here on (same bucket walk, no group of their own); all fixed: row done
+              const int t0 = __popc(fixed);
+              if (t0 >= nt) {
+                s_restart = 2;   // nothing left to select
+              } else {
+                for (int t = 0; t < t0; ++t) R.rank[t] = R.rank[t0];
+              }
             }
+            R.fixed_mask = fixed;
           }
         }
       }
       __syncthreads();
     }
-    const bool restart = s_restart != 0;
+    const bool all_fixed = s_restart == 2;
+    const bool restart = s_restart == 1;
     // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
     // holding its rank
     const int w = 64 - rb < 8 ? 64 - rb : 8;
-    if (!extremes_only && !restart && warp < nt && R.n_valid > 0) {
+    if (!extremes_only && !restart && !all_fixed && warp < nt && R.n_valid > 0) {
       const uint32_t* h = H + R.group[warp] * 256;
       uint32_t c[8];
       uint32_t local = 0;
@@ -598,7 +644,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
       } else if (restart) {
         nrb = 0;
         R.adaptive = 0;
-      } else if (R.n_valid <= 0) {
+      } else if (R.n_valid <= 0 || all_fixed) {
         nrb = 64;
       }
       R.rb = nrb;
@@ -639,8 +685,9 @@ __device__ __forceinline__ double finish_value(const SelRow& R, int k) {
   const QuantileSpec& spec = R.d.spec;
   const int64_t nv = R.n_valid;
   if (nv <= 0) return CUDART_NAN;
-  const double a = value_of(R.prefix[R.slot[2 * k]]);
-  const double b = value_of(R.prefix[R.slot[2 * k + 1]]);
+  const int sa = R.slot[2 * k], sb = R.slot[2 * k + 1];
+  const double a = ((R.fixed_mask >> sa) & 1u) ? 0.0 : value_of(R.prefix[sa]);   // fixed: +0.0 (kZeroKey)
+  const double b = ((R.fixed_mask >> sb) & 1u) ? 0.0 : value_of(R.prefix[sb]);
   if (spec.median) return (nv & 1) ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
   const double q = spec.q[k];
   const double vi = __dmul_rn((double)(nv - 1), q);
@@ -987,19 +1034,51 @@ cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, vo
   return cudaGetLastError();
 }
 
-cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st) {
-  const unsigned chunks = (unsigned)((max_n + kChunk - 1) / kChunk);
-  if (rows <= 0 || chunks == 0) return cudaSuccess;
+// elements per CTA of a full scan: 16 K for rows of up to 16 M elements, else the row cut into
+// kMaxChunksPerRow pieces (a multiple of the 4 * kHistThreads-element tile of scan_elements)
+static int chunk_for(int64_t max_n) {
+  if (max_n <= (int64_t)kChunk * kMaxChunksPerRow) return kChunk;
+  const int64_t c = (max_n + kMaxChunksPerRow - 1) / kMaxChunksPerRow;
+  const int64_t tile = 4 * kHistThreads;
+  return (int)((c + tile - 1) / tile * tile);
+}
+
+cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st, int sampled) {
+  if (rows <= 0 || max_n <= 0) return cudaSuccess;
+  int chunk = chunk_for(max_n), stride = 1;
+  unsigned grid = (unsigned)((max_n + chunk - 1) / chunk);
+  if (pass == 0) {
+    // adaptive calls only sample the rows for their extreme keys in pass 0: ~64 pieces of 16 K
+    // elements per long row. `sampled` = the caller knows the call is adaptive (grid of sample CTAs
+    // only); otherwise the piece grid is launched and the CTAs off the sample exit at once.
+    const int64_t pieces = (max_n + kChunk - 1) / kChunk;
+    chunk = kChunk;
+    if (sampled) {
+      stride = (int)(pieces / 64 > kSampleStride ? pieces / 64 : kSampleStride);
+      const int64_t g = (pieces + stride - 1) / stride;
+      grid = (unsigned)(g > kSampleMinChunks ? g : (pieces < kSampleMinChunks ? pieces : kSampleMinChunks));
+    } else {
+      stride = kSampleStride;   // non-adaptive rows ignore it (pass 0 is their first digit pass) ...
+      grid = (unsigned)pieces;  // ... and need every piece
+      if (max_n > (int64_t)kChunk * kMaxChunksPerRow) {  // long non-adaptive rows: plain chunk grid, stride unused
+        chunk = chunk_for(max_n);
+        grid = (unsigned)((max_n + chunk - 1) / chunk);
+        stride = 1;
+      }
+    }
+  }
   const size_t smem = (size_t)kHistWords * sizeof(uint32_t);
-  k_sel_hist<<<dim3(chunks, (unsigned)rows), kHistThreads, smem, st>>>((SelRow*)state, (uint32_t*)hist,
-                                                                       cand_of(state, rows), pass);
+  k_sel_hist<<<dim3(grid, (unsigned)rows), kHistThreads, smem, st>>>((SelRow*)state, (uint32_t*)hist,
+                                                                     cand_of(state, rows), pass, chunk, stride);
   return cudaGetLastError();
 }
 
 cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st) {
-  const unsigned chunks = (unsigned)((max_n + kChunk - 1) / kChunk);
   if (rows <= 0) return cudaSuccess;
-  if (chunks > 0) k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>((SelRow*)state, cand_of(state, rows));
+  const int chunk = chunk_for(max_n);
+  const unsigned chunks = (unsigned)((max_n + chunk - 1) / chunk);
+  if (chunks > 0)
+    k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>((SelRow*)state, cand_of(state, rows), chunk);
   k_sel_collect_finish<<<rows, 32, 0, st>>>((SelRow*)state);
   return cudaGetLastError();
 }
@@ -1031,8 +1110,9 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
   }
   cudaError_t e = launch_sel_begin(rows, desc_host, state, hist, st, /*adaptive=*/1, /*fused=*/1);
   ++*n_launches;
-  for (int pass = 0; pass < kFullPasses && e == cudaSuccess; ++pass) {
-    e = launch_sel_hist(rows, max_n, pass, state, hist, st);
+  const int full = select_full_passes_for(max_n);
+  for (int pass = 0; pass < full && e == cudaSuccess; ++pass) {
+    e = launch_sel_hist(rows, max_n, pass, state, hist, st, /*sampled=*/1);
     *n_launches += max_n > 0;
     if (e == cudaSuccess) e = launch_sel_advance(rows, max_nq, pass, state, hist, st);
     ++*n_launches;
@@ -1050,6 +1130,7 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
 }
 
 int select_full_passes() { return kFullPasses; }
+int select_full_passes_for(int64_t n_global_max) { return n_global_max > kLongRow ? kFullPassesLong : kFullPasses; }
 
 size_t select_exchange_words(int rows, int world) {
   rows = rows > 0 ? rows : 1;

@@ -29,9 +29,11 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
 // the same select, one pass at a time (a multi-GPU caller all-reduces `hist` between hist and advance)
 cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, void* hist, cudaStream_t st,
                              int adaptive = 0, int fused = 0);
-cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st);
+cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st,
+                            int sampled = 0);
 cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st);
 int select_full_passes();
+int select_full_passes_for(int64_t n_global_max);
 // pooled tail for path shards on several GPUs (see "candidate exchange" in mcr_reduce.cu)
 size_t select_exchange_words(int rows, int world);
 void select_exchange_layout(int rows, int world, int64_t at[4]);

@@ -144,6 +144,7 @@ SIGNATURES = {
     "mcr_select_state_bytes": (_I64, [_I32]),
     "mcr_select_hist_bytes": (_I64, [_I32]),
     "mcr_select_full_passes": (_I32, []),
+    "mcr_select_full_passes_for": (_I32, [_I64]),
     "mcr_select_exchange_words": (_I64, [_I32, _I32]),
     "mcr_select_exchange_layout": (None, [_I32, _I32, C.POINTER(_I64)]),
     "mcr_quantiles_rows": (C.c_int, [_VP, C.POINTER(SelectRow), _I32, _VP, _VP, _VP]),
@@ -373,7 +374,9 @@ class Context:
             self._check(self.lib.mcr_select_step(self.handle, kind, p, arr, n_rows, _ptr(state), _ptr(hist),
                                                  _ptr(out if buf is None else buf), _ptr(counts), _stream_handle()))
 
-        full = int(self.lib.mcr_select_full_passes())
+        # global row length: the shards are balanced (shard_range), so local max x world
+        n_max = int(arr_np["n"].max()) * int(world or 1)
+        full = int(self.lib.mcr_select_full_passes_for(n_max))
         adaptive = all_reduce_min is not None
         if adaptive and world is not None:
             # pooled tail: `full` all-reduced passes at most, then the ranks pool their candidates
@@ -389,7 +392,7 @@ class Context:
 
             step(0, 3)
             for p in range(full):
-                step(1, p)
+                step(1, p | (0x100 if p == 0 else 0))   # pass 0: only the sample CTAs
                 if p == 0:
                     ext = torch.empty((n_rows, 2), dtype=torch.int64, device=dev)
                     step(5, 0, ext)
@@ -414,7 +417,7 @@ class Context:
         for p in range(10 if adaptive else 8):
             if p == full:
                 step(4)  # COLLECT: candidates of the resolved prefixes (local shard)
-            step(1, p)
+            step(1, p | (0x100 if (p == 0 and adaptive) else 0))
             if p == 0 and adaptive:  # global row extremes -> skip the key bits every element shares
                 ext = torch.empty((n_rows, 2), dtype=torch.int64, device=dev)
                 step(5, 0, ext)

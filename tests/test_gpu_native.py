@@ -188,6 +188,54 @@ def test_quantiles_match_pandas_bit_for_bit(n):
     assert (np.isnan(want_med) and np.isnan(med.item())) or med.item() == want_med
 
 
+def _zero_padded_rows(n, rng):
+    """Band-row shapes of config #5: a bulk of positive balances next to a mass of exact zeros
+    (failed paths pad +0.0, simulation.py:905-912)."""
+    base = np.exp(rng.normal(17, 0.8, n))
+    rows = []
+    for frac in (0.001, 0.022, 0.5, 0.99):
+        r = base.copy(); r[rng.random(n) < frac] = 0.0
+        rows.append(r)                                         # 0-3: targets fall on both sides of the zero mass
+    rows.append(np.zeros(n))                                   # 4: every path failed
+    r = base.copy(); r[rng.random(n) < 0.3] = 0.0; r[rng.random(n) < 0.02] = 1e-9
+    rows.append(r)                                             # 5: the mass below the bulk is NOT only zeros -> restart
+    r = base.copy(); r[rng.random(n) < 0.2] = 0.0; r[rng.random(n) < 0.1] *= -1.0
+    rows.append(r)                                             # 6: zeros between negative and positive keys
+    r = base.copy(); r[rng.random(n) < 0.3] = 0.0; r[rng.random(n) < 0.3] = np.nan
+    rows.append(r)                                             # 7: with NaN (skipped)
+    r = np.zeros(n); r[: 3] = base[: 3]
+    rows.append(r)                                             # 8: three survivors
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("n", [300_000, 16384 * 1024 + 12_345])
+def test_quantiles_of_rows_with_a_mass_of_zeros(n):
+    """The adaptive start takes the extremes over the non-zero keys and resolves targets inside the
+    zero mass directly; rows of more than 16 M elements are scanned in 1024 long chunks."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    x = _zero_padded_rows(n, rng)
+    if n > 1_000_000:
+        x = x[[1, 3, 5]]
+    q = [0.01, 0.05, 0.10, 0.25, 0.50, 0.75, 0.90, 0.95, 0.99]
+    sim = make_sim(scenarios.TEST_BASE)
+    rows = x.shape[0]
+    out = torch.empty((rows, len(q)), dtype=torch.float64, device="cuda")
+    cnt = torch.empty(rows, dtype=torch.int64, device="cuda")
+    xd = _dev(x)
+    sim.native_context.quantiles(xd, n, n, rows, q, out, counts=cnt)
+    want = np.stack([pd.Series(r).quantile(q).to_numpy() for r in x])
+    got = out.cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True), np.argwhere(~((got == want) | (np.isnan(got) & np.isnan(want))))
+    assert cnt.cpu().tolist() == [int(np.count_nonzero(~np.isnan(r))) for r in x]
+    mask = rng.random(n) < 0.6
+    med = torch.empty((rows, 1), dtype=torch.float64, device="cuda")
+    sim.native_context.quantiles(xd, n, n, rows, [0.5], med, mask=_dev(mask, np.uint8), median=True)
+    want_med = np.array([pd.Series(r[mask]).median() for r in x])
+    assert np.array_equal(med.cpu().numpy()[:, 0], want_med, equal_nan=True)
+
+
 def test_quantiles_of_long_rows_are_exact_whatever_the_sampled_extremes_miss():
     """Rows longer than 8 chunks take their adaptive start from a SAMPLE (every 16th chunk of
     16384 elements); the first digit pass accounts for everything outside the sampled prefix

@@ -154,6 +154,27 @@ def test_pooled_tail_select_equals_global_quantiles(splits):
     assert unresolved == 0 and outs[0].item() == pd.Series(x[0]).median()
 
 
+def test_pooled_tail_finishes_rows_with_a_mass_of_zeros():
+    """Config #5's band rows (zero-padded failures next to a bulk of balances) over three logical
+    ranks: the pooled tail must finish every row — the fallback is for pathological data only."""
+    import torch
+
+    from test_gpu_native import _zero_padded_rows
+
+    splits = (70_000, 130_001, 99_999)
+    n = sum(splits)
+    x = _zero_padded_rows(n, np.random.default_rng(6))
+    q = [0.01, 0.05, 0.10, 0.25, 0.50, 0.75, 0.90, 0.95, 0.99]
+    sim = make_sim(scenarios.TEST_BASE)
+    bounds = np.cumsum((0,) + splits)
+    shards = [torch.from_numpy(np.ascontiguousarray(x[:, a:b])).to("cuda") for a, b in zip(bounds, bounds[1:])]
+    outs, cnts, unresolved = _logical_pooled_quantiles(sim.native_context, shards, x.shape[0], q)
+    assert unresolved == 0
+    want = np.stack([pd.Series(r).quantile(q).to_numpy() for r in x])
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), want, equal_nan=True)
+
+
 def test_pooled_tail_reports_rows_it_cannot_finish():
     """A dense cluster of distinct values inside a wide key range stays too big for the pool after
     all full passes: every rank reports the row, the caller falls back to the stepwise protocol."""
