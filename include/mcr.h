@@ -357,6 +357,34 @@ int mcr_histogram(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_de
 int mcr_gather_columns(mcr_ctx* ctx, const double* series_dev, int64_t ld, int32_t rows,
                        const int64_t* cols_host, int32_t n_cols, double* out_dev, void* stream);
 
+/* ---- several GPUs of one process ------------------------------------------------ */
+
+/* The reference is driven by a CLI and by FastAPI worker threads (backend/main.py:68-106,
+ * backend/server.py:309,405), so the multi-GPU form its callers can reach is ONE process with one
+ * mcr_ctx per device (one host thread each). Path shards never exchange per-path data; the few
+ * small reductions (success counts, digit histograms and pooled candidates of the distributed
+ * select, histograms) are all-reduced by hand-written kernels over NVLink / NVSwitch peer memory:
+ * one mcr_comm per context, connected to its peers once. All ranks call mcr_comm_all_reduce with
+ * the same op and element count in the same order; the call only enqueues a kernel on `stream`
+ * and the result replaces buf_dev on every rank. n * width must not exceed max_bytes. */
+#define MCR_COMM_SUM_I32 0
+#define MCR_COMM_SUM_I64 1
+#define MCR_COMM_MIN_I64 2
+#define MCR_COMM_MAX_I64 3
+#define MCR_COMM_SUM_F64 4
+#define MCR_COMM_MIN_F64 5
+#define MCR_COMM_MAX_F64 6
+typedef struct mcr_comm mcr_comm;
+int mcr_comm_create(mcr_ctx* ctx, int64_t max_bytes, mcr_comm** out_comm);
+/* comms[world]: every rank's communicator (same process), comms[rank] == comm; enables peer access. */
+int mcr_comm_connect(mcr_comm* comm, int32_t rank, int32_t world, mcr_comm* const* comms);
+int mcr_comm_all_reduce(mcr_comm* comm, int32_t op, void* buf_dev, int64_t n, void* stream);
+/* non-zero: a kernel of this rank gave up waiting for a peer (~2 s); the number of that call */
+int32_t mcr_comm_status(const mcr_comm* comm);
+int64_t mcr_comm_calls(const mcr_comm* comm);
+const char* mcr_comm_last_error(const mcr_comm* comm);
+int mcr_comm_destroy(mcr_comm* comm);
+
 /* ---- measurement ----------------------------------------------------------------------- */
 
 /* DFMA-chain microbenchmark: FP64-pipe issue slots (lane-instructions) per second on this

@@ -2,10 +2,11 @@
 
     python -m monte_carlo_retirement_b200.build [--force]
 
-Four translation units, two arithmetic contracts:
+Five translation units, two arithmetic contracts:
   mcr_kernels_strict.cu  -fmad=false   parity build (reference operation order)
   mcr_kernels_fast.cu    -fmad=true    throughput build
   mcr_reduce.cu          -fmad=false   numpy-exact interpolation arithmetic
+  mcr_comm.cu                          all-reduce over NVLink peer memory (several GPUs, one process)
   mcr_api.cu                           extern "C" boundary (include/mcr.h)
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
@@ -34,6 +35,7 @@ UNITS = [
     ("mcr_kernels_strict.cu", ["-fmad=false"]),
     ("mcr_kernels_fast.cu", ["-fmad=true"]),
     ("mcr_reduce.cu", ["-fmad=false"]),
+    ("mcr_comm.cu", []),
     ("mcr_api.cu", []),
 ]
 
@@ -89,7 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=5) as ex:
         objs = list(ex.map(compile_one, UNITS))
     tmp = LIB_PATH + ".tmp"
     r = subprocess.run([nvcc, *ARCH, "-shared", "-o", tmp, *objs], capture_output=True, text=True)

@@ -194,6 +194,8 @@ double mcr_small_returns_bound(const mcr_ctx* ctx) {
   return ctx->dev.exp_small == 2 ? 0.05 : (ctx->dev.exp_small == 1 ? 0.1 : 0.0);
 }
 
+int mcr_comm_device_of(const mcr_ctx* ctx) { return ctx ? ctx->device : 0; }  // mcr_comm.cu
+
 int32_t mcr_last_variant(const mcr_ctx* ctx) { return ctx ? ctx->last_variant : -1; }
 
 int64_t mcr_launch_count(const mcr_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -98,13 +98,14 @@ constexpr int kSampleStride = 16;   // adaptive pass 0 reads every 16th chunk of
 constexpr int kSampleMinChunks = 8; // ... rows of up to 8 chunks are read whole
 constexpr int kMaxCommonBits = 56;  // the first digit pass always has a digit left to count with
 constexpr int kBelowAt = 256, kAboveAt = 257;  // H slots of the keys outside the sampled prefix (first digit pass)
-constexpr int kBelowOtherAt = 258;             // ... and of the keys below it that are not +0.0
+constexpr int kBelowZeroAt = 258, kBelowNegAt = 259;  // ... of which: exactly +0.0 / smaller than +0.0 (negative)
 // The engine pads the yearly series of a failed path with +0.0 (simulation.py:905-912) and clamps final
 // balances at 0, so rows hold a mass of exact zeros next to a bulk of positive balances. Zeros share
 // only the sign bit with the bulk: a common prefix over all keys would be worthless and the zero
 // bucket never shrinks. The adaptive start therefore takes the row extremes over the keys != +0.0,
-// the first digit pass counts the zeros as `below`, and a target whose rank falls into a `below`
-// mass made of zeros only IS +0.0 — resolved on the spot.
+// the first digit pass counts the keys below the prefix in three classes (negative, +0.0, small
+// positive), and a target whose rank falls among the zeros IS +0.0 — resolved on the spot. (Keys
+// the sample missed just below the bulk or below zero only matter if a target lands on them.)
 constexpr uint64_t kZeroKey = 0x8000000000000000ull;
 
 __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ hist, const RowDesc* __restrict__ desc,
@@ -323,7 +324,8 @@ __device__ __forceinline__ void first_digit_elements(const Probe& P, const doubl
       } else {  // first differing bit decides the side: the key has a 1 where the prefix has a 0 <=> above
         const uint64_t kp = k & (((uint64_t)P.m_hi << 32) | P.m_lo), pp = ((uint64_t)P.p_hi << 32) | P.p_lo;
         id = kp > pp ? kAboveAt : kBelowAt;
-        if (id == kBelowAt && k != kZeroKey) red_shared_add(P.a_hist + (uint32_t)kBelowOtherAt * 4u, 1u);  // (rare)
+        if (id == kBelowAt && k <= kZeroKey)   // zero-padded failures (common), negative keys (rare)
+          red_shared_add(P.a_hist + (uint32_t)(k == kZeroKey ? kBelowZeroAt : kBelowNegAt) * 4u, 1u);
       }
     }
     const int id0 = __shfl_sync(0xffffffffu, id, 0);
@@ -552,18 +554,20 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
           const int64_t below = first_digit ? (int64_t)H[kBelowAt] : 0, above = first_digit ? (int64_t)H[kAboveAt] : 0;
-          const bool below_is_zeros = first_digit && H[kBelowOtherAt] == 0;
+          const int64_t below_neg = first_digit ? (int64_t)H[kBelowNegAt] : 0;
+          const int64_t below_zero = first_digit ? (int64_t)H[kBelowZeroAt] : 0;
           set_target_ranks(R, part + below + above);
           if (!adaptive) {
             for (int t = 0; t < nt; ++t) { R.prefix[t] = 0; R.group[t] = 0; }
           } else {
-            // ranks inside the prefix bucket. A target below it is +0.0 when the whole `below` mass is
-            // (zero-padded failures); any other target outside the bucket restarts the row.
+            // ranks inside the prefix bucket. A target below it is +0.0 when its rank falls among the
+            // zeros of the `below` mass (zero-padded failures: negative keys first, then the zeros,
+            // then small positives); any other target outside the bucket restarts the row.
             uint32_t fixed = 0;
             for (int t = 0; t < nt; ++t) {
               if (R.n_valid > 0) {
                 if (R.rank[t] < below) {
-                  if (below_is_zeros) fixed |= 1u << t; else s_restart = 1;
+                  if (R.rank[t] >= below_neg && R.rank[t] < below_neg + below_zero) fixed |= 1u << t; else s_restart = 1;
                 } else if (R.rank[t] >= below + part) {
                   s_restart = 1;
                 }
@@ -574,8 +578,9 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
               fixed = 0;
               for (int t = 0; t < nt; ++t) { R.rank[t] += below; R.prefix[t] = 0; R.group[t] = 0; R.bcount[t] = R.n_valid; }
             } else if (fixed) {
-              // targets are rank-sorted, so the fixed ones come first: they shadow the first live
-              // target from here on (same bucket walk, no group of their own); all fixed: row done
+              // targets are rank-sorted and every target below the bucket is fixed here (else the row
+              // restarted), so the fixed ones come first: they shadow the first live target from
+              // here on (same bucket walk, no group of their own); all fixed: row done
               const int t0 = __popc(fixed);
               if (t0 >= nt) {
                 s_restart = 2;   // nothing left to select

@@ -155,6 +155,13 @@ SIGNATURES = {
     "mcr_histogram": (C.c_int, [_VP, _VP, _VP, _I64, _D, _I32, _I32, _VP, _VP, _VP]),
     "mcr_gather_columns": (C.c_int, [_VP, _VP, _I64, _I32, C.POINTER(_I64), _I32, _VP, _VP]),
     "mcr_fp64_peak_slots_per_s": (C.c_int, [_VP, C.POINTER(_D)]),
+    "mcr_comm_create": (C.c_int, [_VP, _I64, C.POINTER(_VP)]),
+    "mcr_comm_connect": (C.c_int, [_VP, _I32, _I32, C.POINTER(_VP)]),
+    "mcr_comm_all_reduce": (C.c_int, [_VP, _I32, _VP, _I64, _VP]),
+    "mcr_comm_status": (_I32, [_VP]),
+    "mcr_comm_calls": (_I64, [_VP]),
+    "mcr_comm_last_error": (C.c_char_p, [_VP]),
+    "mcr_comm_destroy": (C.c_int, [_VP]),
 }
 
 _lib = None

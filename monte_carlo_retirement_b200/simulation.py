@@ -744,6 +744,13 @@ class RetirementMonteCarloSimulator:
         out16 = torch.empty((len(desc), 16), **f64)
         cnt_all = torch.empty(len(desc), dtype=torch.int64, device=dev)
         flag = self._select(desc, out16, cnt_all, stepwise=stepwise)
+        if flag is not None and len(plan) > 1:
+            # series swept in several passes: later passes release this batch's series, so nothing is
+            # deferred — every select of the call is verified (and repeated stepwise) on the spot
+            if int(flag.item()) != 0:
+                self.select_fallbacks += 1
+                self._select(desc, out16, cnt_all, stepwise=True)
+            flag = None
         small[0:3].copy_(out16[0:3, 0])
         cnt.copy_(cnt_all[0:3])
         small[3:3 + nf].copy_(out16[3, :nf])

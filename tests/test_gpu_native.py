@@ -205,7 +205,10 @@ def _zero_padded_rows(n, rng):
     rows.append(r)                                             # 7: with NaN (skipped)
     r = np.zeros(n); r[: 3] = base[: 3]
     rows.append(r)                                             # 8: three survivors
-    return np.stack(rows)
+    r = base.copy(); r[rng.random(n) < 0.03] = 0.0
+    far = rng.choice(n, 5, replace=False); r[far[:3]] = 1e-3; r[far[3:]] = -2.0
+    rows.append(r)                                             # 9: zeros + five keys far from the bulk (below AND
+    return np.stack(rows)                                      #    above zero) that a sample is unlikely to see
 
 
 @pytest.mark.parametrize("n", [300_000, 16384 * 1024 + 12_345])
@@ -217,7 +220,7 @@ def test_quantiles_of_rows_with_a_mass_of_zeros(n):
     rng = np.random.default_rng(5)
     x = _zero_padded_rows(n, rng)
     if n > 1_000_000:
-        x = x[[1, 3, 5]]
+        x = x[[1, 3, 9]]
     q = [0.01, 0.05, 0.10, 0.25, 0.50, 0.75, 0.90, 0.95, 0.99]
     sim = make_sim(scenarios.TEST_BASE)
     rows = x.shape[0]
