@@ -233,6 +233,18 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
                      int32_t n_candidates, int64_t first_path, int64_t n_paths, uint32_t flags,
                      int64_t* success_counts_dev, uint64_t* executed_months_dev, void* stream);
 
+/* Multi-scenario batching (no reference counterpart — the reference runs one
+ * scenario per process): n_items (scenario, working_months) pairs evaluated on the SAME Philox
+ * streams of this context (common random numbers across scenarios: a sensitivity grid's points
+ * differ by their parameters, not by their luck) in one launch per kernel variant present.
+ * scenarios_host[k] is flattened like the argument of mcr_create (the context's own scenario
+ * plays no role; its seed and device do). success_counts_dev[k] / executed_months_dev[k] (may be
+ * NULL) are ACCUMULATED (+=). */
+int mcr_sweep_batch(mcr_ctx* ctx, int seed_stream, const mcr_params* scenarios_host,
+                    const int32_t* working_months_host, int32_t n_items, int64_t first_path,
+                    int64_t n_paths, uint32_t flags, int64_t* success_counts_dev,
+                    uint64_t* executed_months_dev, void* stream);
+
 /* ---- device aggregations (a14/a16/a19 of SURVEY §8) ------------------------------------ */
 
 #define MCR_SEL_MEDIAN 0x1u /* np.median rule: mean of the two middle order statistics

@@ -433,6 +433,94 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
   return MCR_OK;
 }
 
+int mcr_sweep_batch(mcr_ctx* ctx, int seed_stream, const mcr_params* scenarios_host, const int32_t* working_months_host,
+                    int32_t n_items, int64_t first_path, int64_t n_paths, uint32_t flags, int64_t* success_counts_dev,
+                    uint64_t* executed_months_dev, void* stream) {
+  if (!ctx || !scenarios_host || !working_months_host || !success_counts_dev) return fail(ctx, MCR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n_items < 0 || n_items > 65535) return fail(ctx, MCR_EINVAL, "n_items must be in [0, 65535]");
+  if (n_paths < 0 || first_path < 0) return fail(ctx, MCR_EINVAL, "negative path range");
+  if (seed_stream != MCR_STREAM_SEARCH && seed_stream != MCR_STREAM_FINAL) return fail(ctx, MCR_EINVAL, "bad seed stream");
+  if (n_items == 0 || n_paths == 0) return MCR_OK;
+  const bool fast = !(flags & MCR_FLAG_STRICT);
+  // derive every scenario like mcr_create does, and its variant
+  std::vector<DevParams> dev((size_t)n_items);
+  std::vector<int32_t> variant((size_t)n_items);
+  std::vector<int32_t> windows((size_t)n_items * 2 * MCR_MAX_STREAMS);
+  for (int k = 0; k < n_items; ++k) {
+    std::string why;
+    double live_age[MCR_MAX_STREAMS] = {0};
+    int32_t live_dur[MCR_MAX_STREAMS] = {0};
+    if (validate_and_derive(scenarios_host[k], dev[k], live_age, live_dur, why) != MCR_OK)
+      return fail(ctx, MCR_EINVAL, "scenario " + std::to_string(k) + ": " + why);
+    const int32_t wm = working_months_host[k];
+    if (wm < 0 || (int64_t)wm + (int64_t)dev[k].R * 12 > (1 << 24)) return fail(ctx, MCR_EINVAL, "bad working_months");
+    stream_windows(dev[k], scenarios_host[k].current_age, live_age, live_dur, wm, windows.data() + (size_t)k * 2 * MCR_MAX_STREAMS);
+    variant[k] = pick_cfg_index(dev[k], fast, fast ? dev[k].exp_small : 0);
+  }
+  DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch: DevParams[n] | per group: scen | wm | slot | window
+  const size_t per_item = 3 + 2 * MCR_MAX_STREAMS;
+  const size_t dev_bytes = (sizeof(DevParams) * (size_t)n_items + 255) / 256 * 256;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, dev_bytes + (size_t)n_items * per_item * 4, &scratch)) return rc;
+  std::vector<int32_t> h((size_t)n_items * per_item);
+  // one launch per variant present; inside a launch the longest timelines first
+  std::vector<int32_t> order((size_t)n_items);
+  for (int k = 0; k < n_items; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (variant[a] != variant[b]) return variant[a] < variant[b];
+    return working_months_host[a] + 12 * dev[a].R > working_months_host[b] + 12 * dev[b].R;
+  });
+  MCR_CUDA(ctx, cudaMemcpyAsync(scratch, dev.data(), sizeof(DevParams) * (size_t)n_items, cudaMemcpyHostToDevice, st));
+  int32_t* base_dev = (int32_t*)((char*)scratch + dev_bytes);
+  size_t at = 0;
+  struct Group { int cfg; size_t at, count; };
+  std::vector<Group> groups;
+  for (size_t lo = 0; lo < order.size();) {
+    size_t hi = lo;
+    while (hi < order.size() && variant[order[hi]] == variant[order[lo]]) ++hi;
+    const size_t cnt = hi - lo;
+    int32_t* scen = h.data() + at;
+    int32_t* wm = scen + cnt;
+    int32_t* slot = wm + cnt;
+    int32_t* win = slot + cnt;
+    for (size_t j = 0; j < cnt; ++j) {
+      const int k = order[lo + j];
+      scen[j] = k;
+      wm[j] = working_months_host[k];
+      slot[j] = k;
+      std::memcpy(win + j * 2 * MCR_MAX_STREAMS, windows.data() + (size_t)k * 2 * MCR_MAX_STREAMS, sizeof(int32_t) * 2 * MCR_MAX_STREAMS);
+    }
+    groups.push_back({variant[order[lo]], at, cnt});
+    at += cnt * per_item;
+    lo = hi;
+  }
+  MCR_CUDA(ctx, cudaMemcpyAsync(base_dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+  for (const Group& gr : groups) {
+    SweepArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.keys = ctx->keys;
+    A.seed_stream = (uint32_t)seed_stream;
+    A.n_items = (int32_t)gr.count;
+    A.first_path = first_path;
+    A.n_paths = n_paths;
+    A.scenarios = (const DevParams*)scratch;
+    A.scen = base_dev + gr.at;
+    A.wm = A.scen + gr.count;
+    A.slot = A.wm + gr.count;
+    A.window = A.slot + gr.count;
+    A.success_counts = success_counts_dev;
+    A.executed_months = executed_months_dev;
+    MCR_CUDA(ctx, pick(flags).sweep(A, gr.cfg, st));
+    ctx->launches += 1;
+    ctx->last_variant = gr.cfg;
+  }
+  return MCR_OK;
+}
+
 static int make_spec(mcr_ctx* ctx, const double* q_host, int32_t n_q, uint32_t sel_flags, QuantileSpec& spec) {
   if (n_q <= 0 || n_q > kMaxQuantiles) return fail(ctx, MCR_EINVAL, "n_q must be in [1,16]");
   std::memset(&spec, 0, sizeof(spec));

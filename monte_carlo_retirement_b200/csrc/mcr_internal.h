@@ -35,6 +35,21 @@ struct SearchArgs {
   uint64_t* executed_months;      // caller buffer or NULL, accumulated
 };
 
+// Multi-scenario sweep: like SearchArgs, but every item brings its own scenario.
+struct SweepArgs {
+  PhiloxKeys keys;
+  uint32_t seed_stream;
+  int32_t n_items;
+  int64_t first_path, n_paths;
+  const DevParams* scenarios;     // [n_scenarios] device
+  const int32_t* scen;            // [n_items] device: scenario of the item (items of one launch share a variant)
+  const int32_t* wm;              // [n_items] device, sorted longest first
+  const int32_t* slot;            // [n_items] device: index into the caller's arrays
+  const int32_t* window;          // [n_items][2 * MCR_MAX_STREAMS] device
+  int64_t* success_counts;        // caller buffer, accumulated
+  uint64_t* executed_months;      // caller buffer or NULL, accumulated
+};
+
 struct Launchers {
   cudaError_t (*timeline)(const DevParams&, const TimelineArgs&, bool replay, int cfg, cudaStream_t);  // cfg: pick_cfg_index()
   cudaError_t (*search)(const DevParams&, const SearchArgs&, int cfg, cudaStream_t);
@@ -42,6 +57,7 @@ struct Launchers {
                       int64_t n_paths, int32_t n_months, double* shocks, int64_t ld, cudaStream_t);
   cudaError_t (*helper)(const DevParams&, int which, double a, double b, double c, double d, int use_tax,
                         double rate, double e, double* out, cudaStream_t);
+  cudaError_t (*sweep)(const SweepArgs&, int cfg, cudaStream_t);
 };
 
 const Launchers& strict_launchers();

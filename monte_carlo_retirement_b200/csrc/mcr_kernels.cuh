@@ -115,6 +115,35 @@ __global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_search(const __grid_
   }
 }
 
+// Multi-scenario sweep: blockIdx.y = item = (scenario, working_months), blockIdx.x = tile of 128
+// paths of the SAME Philox streams for every item (common random numbers across scenarios:
+// sensitivity grids differ by their parameters, not by their luck). The scenario constants come
+// from global memory (one DevParams per scenario) instead of the launch's constant bank; the
+// host groups the items by compile-time variant, so the lean month steps apply here as well.
+template <bool FAST, class C>
+__global__ void __launch_bounds__(kBlock, MCR_MIN_BLOCKS) k_sweep(const __grid_constant__ SweepArgs A) {
+  const int c = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool valid = i < A.n_paths;
+  const DevParams& P = A.scenarios[A.scen[c]];
+  PathOut o = {};
+  int years_observed = 0;
+  if (valid) {
+    NullSink sink;
+    const uint64_t gp = (uint64_t)(A.first_path + i);
+    PhiloxShock<FAST> sh{A.keys, (uint32_t)gp, (uint32_t)(gp >> 32), 0u, A.seed_stream,
+                         P.rho_f, P.rho_c_f, P.rho, P.rho_c, 0.f, 0.f, 0.f};
+    run_timeline<FAST, C>(P, A.wm[c], A.window + (size_t)c * 2 * MCR_MAX_STREAMS, sh, sink, o, years_observed);
+  }
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t ok = __ballot_sync(0xffffffffu, valid && o.success);
+  if (lane == 0 && ok) atomicAdd((unsigned long long*)A.success_counts + A.slot[c], (unsigned long long)__popc(ok));
+  if (A.executed_months) {
+    const uint32_t ex = warp_sum(valid ? o.executed : 0u);
+    if (lane == 0 && ex) atomicAdd((unsigned long long*)A.executed_months + A.slot[c], (unsigned long long)ex);
+  }
+}
+
 // Native shocks written out in the replay layout — the device analogue of `_draw_shock_path`
 // (simulation.py:452-466); lets the tests replay the Philox draws through the CPU oracle.
 template <bool FAST>
@@ -195,6 +224,22 @@ static cudaError_t launch_search(const DevParams& P, const SearchArgs& A, int cf
     case 6: k_search<true, CfgNoTaxTight><<<grid, kBlock, 0, st>>>(P, A); break;
 #endif
     default: k_search<MCR_FAST != 0, CfgGeneric><<<grid, kBlock, 0, st>>>(P, A); break;
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_sweep(const SweepArgs& A, int cfg, cudaStream_t st) {
+  dim3 grid((unsigned)((A.n_paths + kBlock - 1) / kBlock), (unsigned)A.n_items);
+  switch (cfg) {
+    case 1: k_sweep<MCR_FAST != 0, CfgBothTaxed><<<grid, kBlock, 0, st>>>(A); break;
+    case 2: k_sweep<MCR_FAST != 0, CfgNoTax><<<grid, kBlock, 0, st>>>(A); break;
+#if MCR_FAST
+    case 3: k_sweep<true, CfgBothTaxedSmall><<<grid, kBlock, 0, st>>>(A); break;
+    case 4: k_sweep<true, CfgNoTaxSmall><<<grid, kBlock, 0, st>>>(A); break;
+    case 5: k_sweep<true, CfgBothTaxedTight><<<grid, kBlock, 0, st>>>(A); break;
+    case 6: k_sweep<true, CfgNoTaxTight><<<grid, kBlock, 0, st>>>(A); break;
+#endif
+    default: k_sweep<MCR_FAST != 0, CfgGeneric><<<grid, kBlock, 0, st>>>(A); break;
   }
   return cudaGetLastError();
 }

@@ -4,7 +4,7 @@
 #include "mcr_kernels.cuh"
 namespace mcr {
 const Launchers& fast_launchers() {
-  static const Launchers L = {launch_timeline, launch_search, launch_draw, launch_helper};
+  static const Launchers L = {launch_timeline, launch_search, launch_draw, launch_helper, launch_sweep};
   return L;
 }
 }  // namespace mcr

@@ -40,7 +40,7 @@ class PeerGroup:
     def __init__(self, devices: Sequence[int]):
         self.devices = [int(d) for d in devices]
         self.world = len(self.devices)
-        self.cpu_barrier = threading.Barrier(self.world, timeout=300)  # a rank that died breaks it instead of hanging the others
+        self.cpu_barrier = threading.Barrier(self.world, timeout=60)  # a rank that died breaks it instead of hanging the others
         self.mailbox: Dict[str, Any] = {}
         self.comms: List[Optional[int]] = [None] * self.world
         self.lock = threading.Lock()

@@ -140,6 +140,7 @@ SIGNATURES = {
     "mcr_helper_annual_tax": (C.c_int, [_VP, _D, _D, _D, _D, _D, _D, C.POINTER(_D)]),
     "mcr_draw_shocks": (C.c_int, [_VP, C.c_int, _I64, _I64, _I32, _U32, _VP, _I64, _VP]),
     "mcr_search_batch": (C.c_int, [_VP, C.c_int, C.POINTER(_I32), _I32, _I64, _I64, _U32, _VP, _VP, _VP]),
+    "mcr_sweep_batch": (C.c_int, [_VP, C.c_int, C.POINTER(Params), C.POINTER(_I32), _I32, _I64, _I64, _U32, _VP, _VP, _VP]),
     "mcr_quantiles": (C.c_int, [_VP, _VP, _I64, _I64, _I32, _VP, C.POINTER(_D), _I32, _U32, _VP, _VP, _VP]),
     "mcr_select_state_bytes": (_I64, [_I32]),
     "mcr_select_hist_bytes": (_I64, [_I32]),
@@ -310,6 +311,14 @@ class Context:
         self._check(self.lib.mcr_search_batch(self.handle, seed_stream, arr, len(candidates), first_path, n_paths,
                                               FLAG_STRICT if strict else 0, _ptr(counts), _ptr(executed),
                                               _stream_handle()))
+
+    def sweep_batch(self, seed_stream: int, scenarios: Sequence[Params], working_months: Sequence[int], first_path: int,
+                    n_paths: int, counts, executed=None, strict: bool = False) -> None:
+        n = len(scenarios)
+        arr = (Params * n)(*scenarios)
+        wm = (_I32 * n)(*[int(w) for w in working_months])
+        self._check(self.lib.mcr_sweep_batch(self.handle, seed_stream, arr, wm, n, first_path, n_paths,
+                                             FLAG_STRICT if strict else 0, _ptr(counts), _ptr(executed), _stream_handle()))
 
     # ---- aggregations -----------------------------------------------------------------------
     def quantiles(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, counts=None, mask=None,

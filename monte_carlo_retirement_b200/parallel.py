@@ -179,7 +179,8 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def run_monte_carlo_simulations(self, working_months: int, num_simulations: int):
         """simulation.py:952-1128 over W ranks. Every rank returns the GLOBAL band frames, sample
         paths and observation counts. `summary_df` (N rows x 7 columns, the only N-sized output):
-        rank 0 gets all N_global rows, the other ranks the rows of their own shard.
+        rank 0 gets all N_global rows, the other ranks the rows of their own shard — all of them
+        zero-copy views of one host block, so a shard crosses PCIe exactly once.
 
         No per-path data crosses NVLink: every GPU copies ITS OWN shard of the seven columns over
         ITS OWN PCIe link — underneath the select kernels — into one host block that all ranks of
@@ -206,19 +207,14 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         b.years_to_ruin_into(years)
         produced = torch.cuda.Event()
         produced.record(main)
-        block = self._summary_block(n_global)          # collective: rank 0 picks a free generation
-        stage = self._staging(n, dev) if coll.rank != 0 else None   # private copy backing this rank's own frame
-        copy_stream = self._copy_stream if stage is None else stage["stream"]
+        block = self._summary_block(n_global)          # collective: a generation no rank still views
+        copy_stream = self._copy_stream
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(produced)
             for c in range(5):
                 block.cols[c, lo:lo + n].copy_(b.cols[c], non_blocking=True)
             block.cols[5, lo:lo + n].copy_(years, non_blocking=True)
             block.succ[lo:lo + n].copy_(b.success, non_blocking=True)
-            if stage is not None:
-                stage["cols"][:5].copy_(b.cols, non_blocking=True)
-                stage["cols"][5].copy_(years, non_blocking=True)
-                stage["succ"].copy_(b.success, non_blocking=True)
         years.record_stream(copy_stream)
 
         # ---- global bands (one distributed multi-row select) and the sample paths
@@ -239,11 +235,13 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         small = [bands.cpu().numpy(), wr_bands.cpu().numpy(), real_bands.cpu().numpy(), wr_counts.cpu().numpy()]
         copy_stream.synchronize()
         coll.barrier()                                  # every shard has landed in the shared block
-        self.last_d2h_bytes = n * (6 * 8 + 1) * (1 if stage is None else 2) + (2 * T * nq + R * nw + 2 * k * T + R) * 8
+        self.last_d2h_bytes = n * (6 * 8 + 1) + (2 * T * nq + R * nw + 2 * k * T + R) * 8
+        # views of the block keep its generation busy on this rank (is_free): rank 0 all rows, the
+        # others the rows of their own shard
         if coll.rank == 0:
-            c, succ = block.np_cols, block.np_succ      # views of these keep the generation busy (is_free)
+            c, succ = block.np_cols, block.np_succ
         else:
-            c, succ = stage["cols"].numpy(), stage["succ"].numpy()
+            c, succ = block.np_cols[:, lo:lo + n], block.np_succ[lo:lo + n]
         summary_df = pd.DataFrame({
             "Start Balance": c[0],
             "Final Balance": c[1],
@@ -270,23 +268,26 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         return super()._staging(n, dev)
 
     def _summary_block(self, n_global: int) -> "_SharedSummaryBlock":
-        """The host block of this call: a generation of the right size that no live DataFrame of
-        rank 0 still views, chosen by rank 0 and announced to the others (one tiny broadcast);
-        a new generation is created — shared memory + page-locking, ~0.1 s, once — when none is free."""
+        """The host block of this call: a generation of the right size that no live DataFrame of ANY
+        rank still views — every rank reports which of its generations are free, one tiny
+        all-reduce(MIN) of that mask picks the first common one; a new generation is created
+        (shared memory + page-locking, ~0.1 s, once) when none is free."""
         import torch
 
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self._torch_device())
         coll = self.coll
-        pick = torch.zeros(1, dtype=torch.int64, device=self._torch_device())
-        if coll.rank == 0:
-            free = [i for i, blk in enumerate(self._shared_blocks) if blk.n == n_global and blk.is_free()]
-            pick[0] = free[0] if free else len(self._shared_blocks)
-        idx = int(coll.broadcast0_(pick).item())
-        while len(self._shared_blocks) <= idx:
-            gen = len(self._shared_blocks)
-            n_of = n_global if gen == idx else 0
-            self._shared_blocks.append(_SharedSummaryBlock(coll, self._block_tag(), gen, n_of))
+        slots = 16
+        free = torch.zeros(slots, dtype=torch.int64)
+        for i, blk in enumerate(self._shared_blocks[:slots]):
+            free[i] = 1 if (blk.n == n_global and blk.is_free()) else 0
+        free = coll.min_(free.to(self._torch_device())).cpu()
+        hits = torch.nonzero(free).flatten().tolist()
+        idx = hits[0] if hits else len(self._shared_blocks)
+        if idx >= slots:   # every generation busy: results are being hoarded; recycle the oldest size class
+            raise RuntimeError("more than 16 live results of the sharded run_monte_carlo_simulations")
+        if idx == len(self._shared_blocks):
+            self._shared_blocks.append(_SharedSummaryBlock(coll, self._block_tag(), idx, n_global))
         return self._shared_blocks[idx]
 
     def _block_tag(self) -> str:

@@ -856,6 +856,40 @@ class RetirementMonteCarloSimulator:
         """Hook for multi-GPU sharding (parallel.ShardedSimulator overrides): identity here."""
         return counts
 
+    # ---- multi-scenario batching (SURVEY §8f rank 4) --------------------------------------------
+    def sweep_success_counts(self, scenarios: Sequence[Any], working_months: Union[int, Sequence[int]],
+                             num_simulations: int, *, first_path: int = 0, with_executed: bool = False):
+        """Success counts of MANY scenarios (Config objects: a parameter sweep / sensitivity grid)
+        in one launch per kernel variant, every scenario on the SAME Philox streams as this
+        simulator (its main seed and active seed stream): the points of the grid differ by their
+        parameters, not by their luck, so differences between them are far less noisy than between
+        independent runs. `working_months`: one value for all, or one per scenario. The reference
+        has no counterpart (one scenario per process); a scenario's count equals what a simulator
+        built for it with the same seed returns from `batched_success_counts`."""
+        import torch
+
+        scen = list(scenarios)
+        wms = [int(working_months)] * len(scen) if isinstance(working_months, int) else [int(w) for w in working_months]
+        if len(wms) != len(scen):
+            raise ValueError("working_months must be one value or one per scenario")
+        dev = self._torch_device()
+        counts = torch.zeros(len(scen), dtype=torch.int64, device=dev)
+        executed = torch.zeros(len(scen), dtype=torch.int64, device=dev) if with_executed else None
+        if scen:
+            lo, n = self._shard(int(num_simulations))
+            self.native_context.sweep_batch(self._seed_stream_id(), [params_from_model(c) for c in scen], wms,
+                                            int(first_path) + lo, n, counts, executed=executed, strict=self.strict)
+            counts = self._reduce_counts(counts)
+            if with_executed:
+                executed = self._reduce_counts(executed)
+        return (counts, executed) if with_executed else counts
+
+    def sweep_success_probabilities(self, scenarios: Sequence[Any], working_months: Union[int, Sequence[int]],
+                                    num_simulations: int) -> List[float]:
+        """`_success_probability` (simulation.py:1130-1136) of every scenario of a sweep, in percent."""
+        counts = self.sweep_success_counts(scenarios, working_months, num_simulations)
+        return [float(c / int(num_simulations) * 100.0) for c in counts.cpu().tolist()]
+
     def find_minimum_working_months(self, verbose: bool = True,
                                     progress_callback: Optional[Callable[[dict], None]] = None
                                     ) -> Tuple[int, float, List[Dict[str, float]]]:

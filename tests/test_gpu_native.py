@@ -548,3 +548,37 @@ def test_concurrent_simulators_and_pipelined_reductions_do_not_share_scratch():
     assert got_path.keys() == want_path.keys()
     for k in want_path:   # the withdrawal-rate list of a failing path carries NaN
         assert np.array_equal(np.asarray(got_path[k], dtype=float), np.asarray(want_path[k], dtype=float), equal_nan=True), k
+
+
+def test_scenario_sweep_equals_one_simulator_per_scenario():
+    """Multi-scenario batching: many Configs in one launch per kernel variant, on the
+    sweeping simulator's Philox streams == one simulator per scenario with the same seed. The grid
+    mixes kernel variants (both taxed / no tax / annual tax), retirement lengths and income streams."""
+    from monte_carlo_retirement_b200.config import Config
+
+    base = dict(scenarios.SYNTH_C3, seed=4711)
+    grid = []
+    for expenses in (8000.0, 12000.0):
+        for vol in (0.02, 0.12):
+            grid.append(dict(base, monthly_expenses=expenses, inv1_returns_volatility=vol))
+    grid.append(dict(scenarios.TEST_BASE, seed=4711, monthly_expenses=4000.0))                  # no tax
+    grid.append(dict(scenarios.SYNTH_C3_ANNUAL, seed=4711))                                      # annual tax: generic variant
+    grid.append(dict(scenarios.JORGE_PLUS, seed=4711))                                           # four income streams, R = 40
+    grid.append(dict(base, retirement_years=25, allocation_inv1_pct=0.3))
+    wms = [240, 240, 200, 200, 36, 240, 75, 180]
+    n = 30_000
+    sweeper = make_sim(base)
+    sweeper.use_search_seeds()
+    counts, executed = sweeper.sweep_success_counts([Config(**g) for g in grid], wms, n, with_executed=True)
+    counts, executed = counts.cpu().tolist(), executed.cpu().tolist()
+    for g, wm, c, ex in zip(grid, wms, counts, executed):
+        one = make_sim(g)
+        one.use_search_seeds()
+        want, want_ex = one.batched_success_counts([wm], n, with_executed=True)
+        assert (c, ex) == (int(want[0]), int(want_ex[0])), (g["scenario"], wm)
+    probs = sweeper.sweep_success_probabilities([Config(**g) for g in grid[:4]], 240, n)
+    assert probs[0] >= probs[1] and probs[0] > probs[2]      # same luck everywhere: cheaper living / lower vol never hurts here
+    # sharded over two logical ranks: the shards' counts add up
+    a = sweeper.sweep_success_counts([Config(**g) for g in grid], wms, 12_000).cpu()
+    b = sweeper.sweep_success_counts([Config(**g) for g in grid], wms, n - 12_000, first_path=12_000).cpu()
+    assert (a + b).tolist() == counts
