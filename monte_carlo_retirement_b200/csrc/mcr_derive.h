@@ -98,7 +98,7 @@ inline int validate_and_derive(const mcr_params& p, DevParams& d, double* live_s
     const double rmax = std::max(d.taxed1 ? d.rate1 : 0.0, d.taxed2 ? d.rate2 : 0.0);
     d.lean_cfg_ok = (d.a1 >= 0.01 && d.a1 <= 0.99 && rmax <= 0.9) ? 1 : 0;
     d.lean_cg = 0.5 * (1.0 - rmax) * std::exp(-0.2);
-    d.lean_guard0 = kLeanMinW * d.lean_cg;
+    d.lean_need_coef = d.E / d.lean_cg;
     // need <= E * level must stay below 1e8 for the 12 months a yearly check covers (|monthly
     // log-return| < 0.1); huge needs could trip the reference's net-cash test by rounding alone
     d.lean_level_max = d.E > 0.0 ? 1e8 / (d.E * std::exp(1.2)) : 1e300;

@@ -49,7 +49,7 @@ struct DevParams {
   int32_t n_streams;       // streams with a positive amount, original order
   int32_t lean_cfg_ok;     // allocation in [0.01, 0.99] and every biting realized-gains rate <= 0.9 (lean months)
   double lean_cg;          // 0.5 * (1 - max biting rate) * exp(-0.2): W * lean_cg > E * level  =>  need < cap / 2
-  double lean_guard0;      // kLeanMinW * lean_cg (folded into the same comparison)
+  double lean_need_coef;   // E / lean_cg: the month is lean-safe iff W > lean_need_coef * level + kLeanMinW
   double lean_level_max;   // yearly check: E * level stays < 1e8 for the next 12 months
   double hrate1, hrate2;   // rate / 2: max(0, g) * rate == (g + |g|) * (rate / 2) exactly
   DevStream streams[MCR_MAX_STREAMS];
@@ -245,6 +245,15 @@ struct Math {
     const double e = fma(-b, x0, 1.0);
     const double e2 = fma(e, e, e);
     return fma(x0, e2, x0);
+  }
+  // lean months, where the quotient does not feed the balance recurrence at first order (the
+  // fraction of the over-weight asset sold — it only sets the tax on the sale —, the real value of
+  // a withdrawal): seed + ONE quadratic step, relative error e^2 ~ 1e-12. The withdrawal fraction
+  // f = need / cap keeps rcp3: its error (always the same sign) would add up to 2e-12 of the
+  // balance over 720 months and show at 1e-9 in the last samples of a path that runs dry.
+  static MCR_DEV double rcp2(double b) {
+    const double x0 = rcp_seed(b);
+    return fma(x0, fma(-b, x0, 1.0), x0);
   }
   // a / b: IEEE in the strict build; a * rcp(b) (<= 2 ulp, no slow-path branch) in the fast one
   static MCR_DEV double div(double a, double b) {
@@ -582,7 +591,7 @@ MCR_DEV double lean_rebalance(const DevParams& P, double nb1, double nb2, double
     const double gs = sell1 ? tx1 : tx2;           // tax due if the WHOLE selling asset were liquidated
     const double cbs = sell1 ? c1 : c2;
     const double as = sell1 ? P.a1 : P.a2;
-    const double fs = fabs(d0) * Math<true>::rcp3(fma(-as, gs, bs));   // fraction of the asset sold
+    const double fs = fabs(d0) * Math<true>::rcp2(fma(-as, gs, bs));   // fraction of the asset sold
     const double tax = fs * gs;
     const double buy = fma(fs, bs, -tax);          // sale - tax: what reaches the other asset
     const double br = fs * cbs;                    // basis removed from the selling asset
@@ -633,7 +642,7 @@ MCR_DEV void lean_decumulate(const DevParams& P, const Factors& cur, double cnet
     // both withdrawals at once (:750-777): net target split by w_i = cap_i / cap and grossed up by
     // b_i / cap_i, i.e. ONE fraction f = need / cap of every balance, basis and latent tax is sold
     const double cap = V - (tx1 + tx2);
-    const double f = need * Math<true>::rcp3(cap);
+    const double f = need * Math<true>::rcp3(cap);   // (feeds the balance every month: full accuracy)
     q = 1.0 - f;
     gross = f * V;
   } else {
@@ -641,7 +650,7 @@ MCR_DEV void lean_decumulate(const DevParams& P, const Factors& cur, double cnet
     q = 1.0;       // unused
   }
   yr_gross += gross;
-  yr_real = fma(gross * level_ret, Math<true>::rcp3(level0), yr_real);      // :778-782
+  yr_real = fma(gross * level_ret, Math<true>::rcp2(level0), yr_real);      // :778-782
   // The rebalance's fraction sold is invariant under the common scale q, so it is computed from
   // the pre-withdrawal values (its reciprocal then runs beside the one above) and q applied once.
   const double Wu = lean_rebalance<C>(P, nb1, nb2, V, tx1, tx2, c1, c2);
@@ -656,7 +665,7 @@ MCR_DEV void lean_decumulate(const DevParams& P, const Factors& cur, double cnet
   b1 = P.a1 * Wn;
   b2 = Wn - b1;
   level = lv;
-  bal = fma(Wn, P.lean_cg, -P.lean_guard0) > P.E * lv;   // W > kLeanMinW and next month's need < cap / 2
+  bal = Wn > fma(P.lean_need_coef, lv, kLeanMinW);   // W > kLeanMinW and next month's need < cap / 2
 }
 
 // (re-)entry test after a general month / at a phase change: on target, big enough, in range
@@ -664,7 +673,7 @@ MCR_DEV bool lean_ready(const DevParams& P, double b1, double b2, double level, 
   const double W = b1 + b2;
   bool ok = P.lean_cfg_ok != 0 && W > kLeanMinW && fabs(fma(-P.a1, W, b1)) <= 1e-13 * W;
   if (retired)
-    ok = ok && fma(W, P.lean_cg, -P.lean_guard0) > P.E * level && level > kLeanLevelMin && level < P.lean_level_max;
+    ok = ok && W > fma(P.lean_need_coef, level, kLeanMinW) && level > kLeanLevelMin && level < P.lean_level_max;
   return ok;
 }
 

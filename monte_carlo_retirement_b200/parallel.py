@@ -195,26 +195,31 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         if n_global <= 0:
             return super().run_monte_carlo_simulations(working_months, n_global)
         lo, n = shard_range(n_global, coll.rank, coll.world)
-        b = self.run_batch_device(working_months, n, series=True, first_path=lo)
-        dev = b.cols.device
-        T, R = b.T, b.R
-        nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
+        dev = self._torch_device()
         f64 = dict(dtype=torch.float64, device=dev)
+        nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
 
-        # ---- the shard's columns start their trip to the host as soon as the timeline kernel is done
+        # ---- the shard's columns start their trip to the host chunk by chunk, as soon as a chunk's
+        # ---- timeline launch is done (underneath the next chunk, then underneath the selects)
         main = torch.cuda.current_stream()
         years = torch.empty(n, **f64)
-        b.years_to_ruin_into(years)
-        produced = torch.cuda.Event()
-        produced.record(main)
         block = self._summary_block(n_global)          # collective: a generation no rank still views
         copy_stream = self._copy_stream
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(produced)
-            for c in range(5):
-                block.cols[c, lo:lo + n].copy_(b.cols[c], non_blocking=True)
-            block.cols[5, lo:lo + n].copy_(years, non_blocking=True)
-            block.succ[lo:lo + n].copy_(b.success, non_blocking=True)
+
+        def copy_out(b, at, cnt):
+            b.years_to_ruin_slice(years, at, cnt)
+            produced = torch.cuda.Event()
+            produced.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(produced)
+                for c in range(5):
+                    block.cols[c, lo + at:lo + at + cnt].copy_(b.cols[c, at:at + cnt], non_blocking=True)
+                block.cols[5, lo + at:lo + at + cnt].copy_(years[at:at + cnt], non_blocking=True)
+                block.succ[lo + at:lo + at + cnt].copy_(b.success[at:at + cnt], non_blocking=True)
+
+        b = self.run_batch_device(working_months, n, series=True, first_path=lo, on_chunk=copy_out,
+                                  chunks=self.e2e_chunks)
+        T, R = b.T, b.R
         years.record_stream(copy_stream)
 
         # ---- global bands (one distributed multi-row select) and the sample paths

@@ -176,6 +176,10 @@ class DeviceBatch:
         assert dst.is_contiguous() and dst.numel() == self.n
         self.ctx.years_to_ruin(self.ruin, self.n, dst)
 
+    def years_to_ruin_slice(self, dst, lo: int, count: int) -> None:
+        """The same for paths [lo, lo + count) only (dst: the whole n-element column)."""
+        self.ctx.years_to_ruin(self.ruin[lo:lo + count], count, dst[lo:lo + count])
+
 
 class DeviceAggregates:
     """Device-resident aggregates of one batch (see RetirementMonteCarloSimulator.aggregates_device)."""
@@ -289,6 +293,9 @@ class RetirementMonteCarloSimulator:
             raise ValueError("search_policy must be 'auto', 'waves', 'probe', 'grid' or 'sequential'")
         self._device_index = device
         self.select_fallbacks = 0  # several GPUs: selects repeated with the stepwise protocol (see DeviceAggregates.to_host)
+        # host-returning batch calls split the timeline launch so that the device-to-host copy of the
+        # summary columns overlaps the simulation (run_batch_device(chunks=...))
+        self.e2e_chunks = int(os.environ.get("MCR_E2E_CHUNKS", "2"))
         self._ctx: Optional[native.Context] = None
         self.last_search_stats: Dict[str, Any] = {}
         logger.info(f"Simulator initialized for scenario '{p.Nickname}' with main seed: {self.main_seed}")
@@ -411,11 +418,15 @@ class RetirementMonteCarloSimulator:
 
     def run_batch_device(self, working_months: int, num_simulations: int, *, first_path: int = 0,
                          series: bool = True, shocks=None, _fast_replay: bool = False,
-                         _small_returns: bool = False) -> DeviceBatch:
+                         _small_returns: bool = False, on_chunk=None, chunks: int = 1) -> DeviceBatch:
         """One launch of the timeline kernel for `num_simulations` paths; everything stays in HBM.
         `shocks` (device tensor [n_months, 3, n]) forces replay of those draws (strict build;
         `_fast_replay` / `_small_returns` are the tests' handles on the fast build and on its
-        MCR_FLAG_SMALL_RETURNS variant, see include/mcr.h)."""
+        MCR_FLAG_SMALL_RETURNS variant, see include/mcr.h).
+        `chunks` > 1 (native draws only) splits the batch into that many launches over contiguous
+        path ranges of the same output buffers and calls `on_chunk(batch, lo, count)` after each —
+        the host-returning callers start a chunk's device-to-host copy while the next chunk is
+        still being simulated. The results are identical (a path depends on its index only)."""
         import torch
 
         ctx = self.native_context
@@ -460,13 +471,38 @@ class RetirementMonteCarloSimulator:
         out.ruin_month_hist = counters[2:].data_ptr()
         if shocks is None and self.rng_mode == "numpy":
             shocks, _ = self._numpy_shocks_device(wm, n)
+        batch = DeviceBatch(n=n, working_months=wm, T=T, R=R, cols=cols, success=success, ruin=ruin,
+                            counters=counters, traj=traj, real=real, wr=wr, shocks=shocks, ctx=ctx)
         if shocks is not None:
             ctx.replay(shocks, int(shocks.shape[2]), int(shocks.shape[0]), wm, n, out, strict=not _fast_replay,
                        small_returns=_small_returns)
-        else:
+            if on_chunk is not None:
+                on_chunk(batch, 0, n)
+            return batch
+        chunks = max(1, min(int(chunks), n // 65536 or 1))
+        if chunks == 1:
             ctx.simulate(self._seed_stream_id(), wm, int(first_path), n, out, strict=self.strict)
-        return DeviceBatch(n=n, working_months=wm, T=T, R=R, cols=cols, success=success, ruin=ruin,
-                           counters=counters, traj=traj, real=real, wr=wr, shocks=shocks, ctx=ctx)
+            if on_chunk is not None:
+                on_chunk(batch, 0, n)
+            return batch
+        # contiguous path ranges, multiples of 1024 paths (whole CTAs, 128-byte-aligned rows)
+        step = (-(-n // chunks) + 1023) // 1024 * 1024
+        for lo in range(0, n, step):
+            cnt = min(step, n - lo)
+            part = native.Outputs()
+            for name, t, width in (("start_balance", cols[0], 8), ("final_balance", cols[1], 8),
+                                   ("first_year_gross", cols[2], 8), ("first_year_real", cols[3], 8),
+                                   ("inflation_at_ret", cols[4], 8), ("success", success, 1), ("ruin_month", ruin, 4),
+                                   ("trajectory", traj, 8), ("real_trajectory", real, 8), ("wr_trajectory", wr, 8)):
+                if t is not None:
+                    setattr(part, name, t.data_ptr() + lo * width)
+            part.series_ld = n
+            part.success_count, part.executed_months = out.success_count, out.executed_months
+            part.ruin_month_hist = out.ruin_month_hist
+            ctx.simulate(self._seed_stream_id(), wm, int(first_path) + lo, cnt, part, strict=self.strict)
+            if on_chunk is not None:
+                on_chunk(batch, lo, cnt)
+        return batch
 
     def _staging(self, n: int, dev):
         """Pinned host destination buffers + the copy stream."""
@@ -585,26 +621,30 @@ class RetirementMonteCarloSimulator:
         if n <= 0:
             return pd.DataFrame(columns=SUMMARY_COLUMNS), None, None, None, None, None, None
         ctx = self.native_context
-        b = self.run_batch_device(working_months, n, series=True)
-        dev = b.cols.device
+        dev = self._torch_device()
+        # the N x 7 summary columns travel to the host (copy engine, side stream) chunk by chunk:
+        # a chunk's copy starts as soon as ITS timeline launch is done, underneath the next chunk's
+        # launch and, for the last one, underneath the select kernels
+        main = torch.cuda.current_stream()
+        stage = self._staging(n, dev)
+        years = torch.empty(n, dtype=torch.float64, device=dev)
+
+        def copy_out(b, lo, cnt):
+            b.years_to_ruin_slice(years, lo, cnt)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(stage["stream"]):
+                stage["stream"].wait_event(done)
+                for col in range(5):   # contiguous row slices: plain async copies
+                    stage["cols"][col, lo:lo + cnt].copy_(b.cols[col, lo:lo + cnt], non_blocking=True)
+                stage["cols"][5, lo:lo + cnt].copy_(years[lo:lo + cnt], non_blocking=True)
+                stage["succ"][lo:lo + cnt].copy_(b.success[lo:lo + cnt], non_blocking=True)
+
+        b = self.run_batch_device(working_months, n, series=True, on_chunk=copy_out, chunks=self.e2e_chunks)
         T, R = b.T, b.R
         nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
         sample_cols = self._sample_columns(n)
         k = len(sample_cols)
-
-        # the N x 7 summary columns start their trip to the host (copy engine, side stream) as
-        # soon as the timeline kernel is done, underneath the select kernels
-        main = torch.cuda.current_stream()
-        stage = self._staging(n, dev)
-        years = torch.empty(n, dtype=torch.float64, device=dev)
-        b.years_to_ruin_into(years)
-        done = torch.cuda.Event()
-        done.record(main)
-        with torch.cuda.stream(stage["stream"]):
-            stage["stream"].wait_event(done)
-            stage["cols"][:5].copy_(b.cols, non_blocking=True)
-            stage["cols"][5].copy_(years, non_blocking=True)
-            stage["succ"].copy_(b.success, non_blocking=True)
         years.record_stream(stage["stream"])
 
         # one small result block: bands (T*7 *2), WR bands (R*5), samples (k*T *2)
