@@ -391,6 +391,13 @@ int mcr_comm_create(mcr_ctx* ctx, int64_t max_bytes, mcr_comm** out_comm);
 /* comms[world]: every rank's communicator (same process), comms[rank] == comm; enables peer access. */
 int mcr_comm_connect(mcr_comm* comm, int32_t rank, int32_t world, mcr_comm* const* comms);
 int mcr_comm_all_reduce(mcr_comm* comm, int32_t op, void* buf_dev, int64_t n, void* stream);
+/* The pooled distributed select (BEGIN ... POOL_TAIL above) in ONE call per rank, with the
+ * all-reduces of `comm` between its steps; rows_host describes this rank's shards.
+ * unresolved_dev[0] receives the number of rows the pool could not finish (identical on all
+ * ranks; non-zero: repeat with the stepwise protocol). */
+int mcr_quantiles_rows_comm(mcr_ctx* ctx, mcr_comm* comm, int32_t rank, int32_t world,
+                            const mcr_select_row* rows_host, int32_t n_rows, double* out_dev,
+                            int64_t* counts_dev, int64_t* unresolved_dev, void* stream);
 /* non-zero: a kernel of this rank gave up waiting for a peer (~2 s); the number of that call */
 int32_t mcr_comm_status(const mcr_comm* comm);
 int64_t mcr_comm_calls(const mcr_comm* comm);

@@ -665,6 +665,69 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
   return MCR_OK;
 }
 
+// The pooled distributed select (mcr.h: MCR_SELECT_POOL_*) driven entirely from here, with the
+// all-reduces of csrc/mcr_comm.cu between its steps: ONE call per rank instead of ~45 (the ranks of
+// a single-process multi-GPU run are Python threads that share one interpreter lock, so every
+// host call saved is serial time saved).
+int mcr_quantiles_rows_comm(mcr_ctx* ctx, mcr_comm* comm, int32_t rank, int32_t world, const mcr_select_row* rows_host,
+                            int32_t n_rows, double* out_dev, int64_t* counts_dev, int64_t* unresolved_dev, void* stream) {
+  if (!ctx || !comm || !out_dev || !unresolved_dev) return fail(ctx, MCR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, MCR_EINVAL, "bad rank / world");
+  std::vector<RowDesc> d;
+  if (int rc = make_descs(ctx, rows_host, n_rows, d)) return rc;
+  int64_t max_n = 0;
+  int max_nq = 1;
+  for (const RowDesc& r : d) {
+    max_n = r.n > max_n ? r.n : max_n;
+    max_nq = r.spec.n_q > max_nq ? r.spec.n_q : max_nq;
+  }
+  DeviceGuard g(ctx->device);
+  if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch: hist | state | exchange buffer | extremes
+  const size_t hb = (quantile_hist_bytes(n_rows) + 255) / 256 * 256;
+  const size_t sb = (quantile_state_bytes(n_rows) + 255) / 256 * 256;
+  const size_t xw = select_exchange_words(n_rows, world);
+  const size_t xb = (xw * 8 + 255) / 256 * 256;
+  void* scratch;
+  if (int rc = ensure_scratch(ctx, st, hb + sb + xb + (size_t)n_rows * 16, &scratch)) return rc;
+  char* base = (char*)scratch;
+  void* hist = base;
+  void* state = base + hb;
+  long long* xbuf = (long long*)(base + hb + sb);
+  long long* ext = (long long*)(base + hb + sb + xb);
+  int64_t at[4];
+  select_exchange_layout(n_rows, world, at);
+  auto reduce = [&](int op, void* buf, int64_t n) -> int {
+    if (mcr_comm_all_reduce(comm, op, buf, n, stream) != MCR_OK)
+      return fail(ctx, MCR_ECUDA, std::string("peer all-reduce: ") + mcr_comm_last_error(comm));
+    return MCR_OK;
+  };
+  MCR_CUDA(ctx, launch_sel_begin(n_rows, d.data(), state, hist, st, /*adaptive=*/1, /*fused=*/1));
+  const int full = select_full_passes_for(max_n * world);   // shards are balanced: global length ~ local x world
+  for (int p = 0; p < full; ++p) {
+    MCR_CUDA(ctx, launch_sel_hist(n_rows, max_n, p, state, hist, st, /*sampled=*/p == 0));
+    if (p == 0) {
+      MCR_CUDA(ctx, launch_sel_extremes(n_rows, state, ext, /*store=*/0, st));
+      if (int rc = reduce(MCR_COMM_MIN_I64, ext, (int64_t)n_rows * 2)) return rc;
+      MCR_CUDA(ctx, launch_sel_extremes(n_rows, state, ext, /*store=*/1, st));
+    }
+    if (int rc = reduce(MCR_COMM_SUM_I32, hist, (int64_t)(quantile_hist_bytes(n_rows) / 4))) return rc;
+    MCR_CUDA(ctx, launch_sel_advance(n_rows, max_nq, p, state, hist, st));
+  }
+  MCR_CUDA(ctx, launch_sel_collect(n_rows, max_n, state, st));
+  MCR_CUDA(ctx, launch_sel_export(n_rows, state, xbuf, rank, world, st));
+  if (int rc = reduce(MCR_COMM_SUM_I64, xbuf + at[0], at[1] - at[0])) return rc;
+  if (int rc = reduce(MCR_COMM_MIN_I64, xbuf + at[1], at[2] - at[1])) return rc;
+  MCR_CUDA(ctx, launch_sel_place(n_rows, state, xbuf, rank, world, st));
+  if (int rc = reduce(MCR_COMM_SUM_I64, xbuf + at[2], at[3] - at[2])) return rc;
+  MCR_CUDA(ctx, launch_sel_tail_pooled(n_rows, state, xbuf, world, out_dev, MCR_MAX_QUANTILES, counts_dev, st));
+  MCR_CUDA(ctx, cudaMemcpyAsync(unresolved_dev, xbuf, 8, cudaMemcpyDeviceToDevice, st));
+  ctx->launches += 9 + 2 * full;
+  return MCR_OK;
+}
+
 int mcr_first_year_rates(mcr_ctx* ctx, const double* start_dev, const double* first_year_real_dev, int64_t n,
                          double* rates_dev, void* stream) {
   if (!ctx || !start_dev || !first_year_real_dev || !rates_dev) return fail(ctx, MCR_EINVAL, "null argument");

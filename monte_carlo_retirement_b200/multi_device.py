@@ -155,6 +155,13 @@ class _Worker(ShardedSimulator):
     """The ShardedSimulator of one device; only the host block of the 7-tuple path differs from the
     torchrun form (process-local pinned memory instead of POSIX shared memory)."""
 
+    def _select(self, specs, out16, counts=None, stepwise: bool = False):
+        # the whole pooled protocol in one library call (the ranks are threads under one interpreter lock)
+        if stepwise:
+            return super()._select(specs, out16, counts, stepwise=True)
+        coll = self.coll
+        return self.native_context.quantiles_rows_comm(coll.handle, coll.rank, coll.world, specs, out16, counts=counts)
+
     def _summary_block(self, n_global: int):
         import torch
 

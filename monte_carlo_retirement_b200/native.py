@@ -159,6 +159,7 @@ SIGNATURES = {
     "mcr_comm_create": (C.c_int, [_VP, _I64, C.POINTER(_VP)]),
     "mcr_comm_connect": (C.c_int, [_VP, _I32, _I32, C.POINTER(_VP)]),
     "mcr_comm_all_reduce": (C.c_int, [_VP, _I32, _VP, _I64, _VP]),
+    "mcr_quantiles_rows_comm": (C.c_int, [_VP, _VP, _I32, _I32, C.POINTER(SelectRow), _I32, _VP, _VP, _VP, _VP]),
     "mcr_comm_status": (_I32, [_VP]),
     "mcr_comm_calls": (_I64, [_VP]),
     "mcr_comm_last_error": (C.c_char_p, [_VP]),
@@ -443,6 +444,18 @@ class Context:
             step(2, p)
         step(3)
         return None
+
+    def quantiles_rows_comm(self, comm_handle, rank: int, world: int, specs, out, counts=None):
+        """The pooled distributed select in one call (several GPUs of this process, csrc/mcr_comm.cu).
+        Returns the 1-element device tensor "rows the pool could not finish"."""
+        import torch
+
+        arr_np = specs if hasattr(specs, "dtype") else self.select_rows(specs)
+        arr = C.cast(arr_np.ctypes.data, C.POINTER(SelectRow))
+        flag = torch.empty(1, dtype=torch.int64, device=out.device)
+        self._check(self.lib.mcr_quantiles_rows_comm(self.handle, comm_handle, rank, world, arr, len(arr_np), _ptr(out),
+                                                     _ptr(counts), _ptr(flag), _stream_handle()))
+        return flag
 
     def quantiles_distributed(self, values, n: int, ld: int, rows: int, q: Sequence[float], out, all_reduce,
                               counts=None, mask=None, median: bool = False) -> None:

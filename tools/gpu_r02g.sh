@@ -1,6 +1,11 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_multi_device.py tests/test_gpu_sharded.py tests/test_gpu_native.py -q -m gpu --timeout 600 -k "multi_device or peer_all_reduce or dropin_uses or mass_of_zeros or nccl" > $O/r02g_pytest.log 2>&1; echo "rc=$?" >> $O/r02g_pytest.log
-tail -30 $O/r02g_pytest.log
-timeout 300 python tools/multi_device_timing.py > $O/r02g_md_timing.json 2> $O/r02g_md_timing.err; cat $O/r02g_md_timing.json; tail -3 $O/r02g_md_timing.err
+timeout 400 python -m pytest tests/test_gpu_multi_device.py tests/test_gpu_sharded.py tests/test_gpu_native.py -q -m gpu --timeout 200 -k "multi_device or peer_all_reduce or dropin_uses or nccl or chunked" > $O/r02g_pytest.log 2>&1; echo "rc=$?" >> $O/r02g_pytest.log
+tail -8 $O/r02g_pytest.log
+timeout 200 python tools/multi_device_timing.py > $O/r02g_md_timing.json 2> $O/r02g_md_timing.err; cat $O/r02g_md_timing.json; tail -3 $O/r02g_md_timing.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 --no-search > $O/r02g_bench_n2.json 2> $O/r02g_bench_n2.err
+python -c "
+import json
+d=json.load(open('$O/r02g_bench_n2.json'))
+print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['e2e']['ms_per_step'])"

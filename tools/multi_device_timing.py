@@ -37,6 +37,8 @@ def main():
     for _ in range(a.reps):
         out = sim.run_monte_carlo_simulations(240, n)
     dt = (time.perf_counter() - t0) / a.reps
+    for _ in range(2):
+        sim.run_aggregates(240, n)
     t0 = time.perf_counter()
     for _ in range(a.reps):
         agg = sim.run_aggregates(240, n)
