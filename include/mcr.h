@@ -303,9 +303,10 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
 /* Optional (BEGIN with pass = 1): after HIST of pass 0, EXTREMES_GET writes every row's local
  * (min, max) key into out_dev as int64[n_rows][2] in an encoding whose element-wise MIN over
  * ranks is the global pair; all-reduce(MIN) it and hand it back with EXTREMES_SET before
- * ADVANCE 0. Pass 0 then only looks at (a sample of) every row for its extreme keys and the
- * select skips the key bits they share — concentrated rows need no extra scans; keys outside
- * that prefix are accounted for exactly by the next pass, which also counts the row. */
+ * ADVANCE 0. Pass 0 then only looks at (a sample of) every row for its extreme keys, and pass 1
+ * histograms ~8 K equal bins laid over that key range (about 13 bits resolved by one scan,
+ * however concentrated the row); keys outside the range are accounted for exactly by the same
+ * pass, which also counts the row. */
 #define MCR_SELECT_EXTREMES_GET 5
 #define MCR_SELECT_EXTREMES_SET 6
 /* Pooled tail (BEGIN with pass = 3: adaptive start + pooled tail). Rows stop scanning as soon as

@@ -41,6 +41,20 @@ struct mcr_ctx {
     size_t bytes = 0;
   };
   std::map<cudaStream_t, Scratch> scratch;
+  // Page-locked staging for the small host arrays a call hands to the device (row descriptors of a
+  // select, candidate lists of a search, scenario blocks of a sweep, column lists). cudaMemcpyAsync
+  // from PAGEABLE memory waits for the stream's earlier work before it stages the source — the
+  // timeline kernel of the same step — so the host could never run more than one kernel ahead of the
+  // device and every hiccup of the calling thread showed up as idle GPU time. A ring of slots, each
+  // guarded by an event recorded behind its copy.
+  static constexpr int kStageSlots = 16;
+  struct Staging {
+    char* p = nullptr;
+    size_t slot_bytes = 0;
+    int next = 0;
+    cudaEvent_t done[kStageSlots] = {};
+    bool in_flight[kStageSlots] = {};
+  } stage;
   // private non-blocking stream of the synchronous host-output entry points (single path,
   // helpers, peak): they must not serialise against other contexts through the legacy stream
   cudaStream_t own_stream = nullptr;
@@ -98,6 +112,48 @@ int ensure_scratch(mcr_ctx* ctx, cudaStream_t st, size_t bytes, void** out) {
     s.bytes = want;
   }
   *out = s.p;
+  return MCR_OK;
+}
+
+// dst_dev[0, bytes) = src_host[0, bytes) behind the work already on `st`, without waiting for it; src_host
+// may be reused as soon as this returns (see mcr_ctx::stage)
+int stage_h2d(mcr_ctx* ctx, cudaStream_t st, void* dst_dev, const void* src_host, size_t bytes) {
+  if (bytes == 0) return MCR_OK;
+  mcr_ctx::Staging& S = ctx->stage;
+  if (bytes > S.slot_bytes) {
+    for (int k = 0; k < mcr_ctx::kStageSlots; ++k)
+      if (S.in_flight[k]) {
+        cudaEventSynchronize(S.done[k]);
+        S.in_flight[k] = false;
+      }
+    if (S.p) cudaFreeHost(S.p);
+    S.p = nullptr;
+    S.slot_bytes = 0;
+    size_t want = 1u << 16;
+    while (want < bytes) want <<= 1;
+    if (cudaHostAlloc(&S.p, want * mcr_ctx::kStageSlots, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      S.p = nullptr;
+      return fail(ctx, MCR_ENOMEM, "page-locked staging allocation of " + std::to_string(want * mcr_ctx::kStageSlots) + " bytes failed");
+    }
+    S.slot_bytes = want;
+    for (int k = 0; k < mcr_ctx::kStageSlots; ++k)
+      if (!S.done[k] && cudaEventCreateWithFlags(&S.done[k], cudaEventDisableTiming) != cudaSuccess)
+        return cuda_fail(ctx, cudaGetLastError(), "cudaEventCreate(staging)");
+  }
+  const int k = S.next;
+  S.next = (S.next + 1) % mcr_ctx::kStageSlots;
+  if (S.in_flight[k]) {
+    cudaError_t e = cudaEventSynchronize(S.done[k]);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaEventSynchronize(staging)");
+  }
+  char* slot = S.p + (size_t)k * S.slot_bytes;
+  std::memcpy(slot, src_host, bytes);
+  cudaError_t e = cudaMemcpyAsync(dst_dev, slot, bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemcpyAsync(staging)");
+  e = cudaEventRecord(S.done[k], st);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaEventRecord(staging)");
+  S.in_flight[k] = true;
   return MCR_OK;
 }
 
@@ -184,6 +240,12 @@ int mcr_destroy(mcr_ctx* ctx) {
         cudaFree(kv.second.p);
       }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (int k = 0; k < mcr_ctx::kStageSlots; ++k)
+      if (ctx->stage.done[k]) {
+        if (ctx->stage.in_flight[k]) cudaEventSynchronize(ctx->stage.done[k]);
+        cudaEventDestroy(ctx->stage.done[k]);
+      }
+    if (ctx->stage.p) cudaFreeHost(ctx->stage.p);
   }
   delete ctx;
   return MCR_OK;
@@ -413,8 +475,7 @@ int mcr_search_batch(mcr_ctx* ctx, int seed_stream, const int32_t* candidates_ho
   cudaStream_t st = (cudaStream_t)stream;
   void* scratch;
   if (int rc = ensure_scratch(ctx, st, h.size() * 4, &scratch)) return rc;
-  // pageable source: the copy is staged before the call returns, so `h` may go out of scope
-  MCR_CUDA(ctx, cudaMemcpyAsync(scratch, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = stage_h2d(ctx, st, scratch, h.data(), h.size() * 4)) return rc;
   SearchArgs A;
   std::memset(&A, 0, sizeof(A));
   A.keys = ctx->keys; A.seed_stream = (uint32_t)seed_stream;
@@ -474,7 +535,7 @@ int mcr_sweep_batch(mcr_ctx* ctx, int seed_stream, const mcr_params* scenarios_h
     if (variant[a] != variant[b]) return variant[a] < variant[b];
     return working_months_host[a] + 12 * dev[a].R > working_months_host[b] + 12 * dev[b].R;
   });
-  MCR_CUDA(ctx, cudaMemcpyAsync(scratch, dev.data(), sizeof(DevParams) * (size_t)n_items, cudaMemcpyHostToDevice, st));
+  if (int rc = stage_h2d(ctx, st, scratch, dev.data(), sizeof(DevParams) * (size_t)n_items)) return rc;
   int32_t* base_dev = (int32_t*)((char*)scratch + dev_bytes);
   size_t at = 0;
   struct Group { int cfg; size_t at, count; };
@@ -498,7 +559,7 @@ int mcr_sweep_batch(mcr_ctx* ctx, int seed_stream, const mcr_params* scenarios_h
     at += cnt * per_item;
     lo = hi;
   }
-  MCR_CUDA(ctx, cudaMemcpyAsync(base_dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = stage_h2d(ctx, st, base_dev, h.data(), h.size() * 4)) return rc;
   for (const Group& gr : groups) {
     SweepArgs A;
     std::memset(&A, 0, sizeof(A));
@@ -560,6 +621,9 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
   void* scratch;
   if (int rc = ensure_scratch(ctx, (cudaStream_t)stream, hb + quantile_state_bytes(n_rows), &scratch)) return rc;
   int n_launches = 0;
+  if (int rc = stage_h2d(ctx, (cudaStream_t)stream, select_desc_area((char*)scratch + hb, n_rows), d.data(),
+                         sizeof(RowDesc) * d.size()))
+    return rc;
   MCR_CUDA(ctx, launch_quantiles_rows(n_rows, d.data(), out_dev, MCR_MAX_QUANTILES, counts_dev,
                                       (char*)scratch + hb, scratch, (cudaStream_t)stream, &n_launches));
   ctx->launches += n_launches;
@@ -588,6 +652,9 @@ int mcr_quantiles(mcr_ctx* ctx, const double* values_dev, int64_t n, int64_t ld,
   void* scratch;
   if (int rc = ensure_scratch(ctx, (cudaStream_t)stream, hb + quantile_state_bytes(rows), &scratch)) return rc;
   int n_launches = 0;
+  if (int rc = stage_h2d(ctx, (cudaStream_t)stream, select_desc_area((char*)scratch + hb, rows), d.data(),
+                         sizeof(RowDesc) * d.size()))
+    return rc;
   MCR_CUDA(ctx, launch_quantiles_rows(rows, d.data(), out_dev, n_q, counts_dev, (char*)scratch + hb, scratch,
                                       (cudaStream_t)stream, &n_launches));
   ctx->launches += n_launches;
@@ -625,8 +692,9 @@ int mcr_select_step(mcr_ctx* ctx, int32_t step, int32_t pass, const mcr_select_r
   cudaStream_t st = (cudaStream_t)stream;
   switch (step) {
     case MCR_SELECT_BEGIN:  // pass != 0: the caller will exchange the row extremes after HIST 0
-      MCR_CUDA(ctx, launch_sel_begin(n_rows, d.data(), state_dev, hist_dev, st, /*adaptive=*/pass & 1,
-                                     /*fused=*/(pass >> 1) & 1));
+      if (int rc = stage_h2d(ctx, st, select_desc_area(state_dev, n_rows), d.data(), sizeof(RowDesc) * d.size())) return rc;
+      MCR_CUDA(ctx, launch_sel_begin(n_rows, state_dev, hist_dev, st, /*adaptive=*/pass & 1,
+                                     /*fused (3: lists are pooled across ranks)=*/((pass >> 1) & 1) ? 3 : 0));
       break;
     case MCR_SELECT_EXTREMES_GET:
     case MCR_SELECT_EXTREMES_SET:
@@ -704,7 +772,8 @@ int mcr_quantiles_rows_comm(mcr_ctx* ctx, mcr_comm* comm, int32_t rank, int32_t 
       return fail(ctx, MCR_ECUDA, std::string("peer all-reduce: ") + mcr_comm_last_error(comm));
     return MCR_OK;
   };
-  MCR_CUDA(ctx, launch_sel_begin(n_rows, d.data(), state, hist, st, /*adaptive=*/1, /*fused=*/1));
+  if (int rc = stage_h2d(ctx, st, select_desc_area(state, n_rows), d.data(), sizeof(RowDesc) * d.size())) return rc;
+  MCR_CUDA(ctx, launch_sel_begin(n_rows, state, hist, st, /*adaptive=*/1, /*fused, pooled lists=*/3));
   const int full = select_full_passes_for(max_n * world);   // shards are balanced: global length ~ local x world
   for (int p = 0; p < full; ++p) {
     MCR_CUDA(ctx, launch_sel_hist(n_rows, max_n, p, state, hist, st, /*sampled=*/p == 0));
@@ -795,7 +864,7 @@ int mcr_gather_columns(mcr_ctx* ctx, const double* series_dev, int64_t ld, int32
   cudaStream_t st = (cudaStream_t)stream;
   void* scratch;
   if (int rc = ensure_scratch(ctx, st, (size_t)n_cols * 8, &scratch)) return rc;
-  MCR_CUDA(ctx, cudaMemcpyAsync(scratch, cols_host, (size_t)n_cols * 8, cudaMemcpyHostToDevice, st));
+  if (int rc = stage_h2d(ctx, st, scratch, cols_host, (size_t)n_cols * 8)) return rc;
   MCR_CUDA(ctx, launch_gather(series_dev, ld, rows, (const int64_t*)scratch, n_cols, out_dev, st));
   ctx->launches += 1;
   return MCR_OK;

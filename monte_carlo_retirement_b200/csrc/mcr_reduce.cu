@@ -71,8 +71,11 @@ struct SelRow {
   int32_t group[kMaxTargets];       // target -> group
   int32_t slot[kMaxTargets];        // (quantile, lo/hi) -> rank-sorted target slot
   uint64_t kmin, kmax;              // row extremes over the keys != +0.0 (pass 0, adaptive mode)
+  uint64_t fbase;                   // first digit pass of an adaptive row: bin = (key >> fshift) - fbase
   uint32_t fixed_mask;              // targets resolved to +0.0 by the first digit pass (see advance_row)
-  uint32_t pad0;
+  int32_t fshift;                   //   (64: no window — nothing sampled, or the row restarted from bit 0)
+  int32_t cap;                      // candidate list capacity of this call (kCandCap; kPoolCap when ranks pool lists)
+  int32_t pad0;
   int64_t n_valid;
   int32_t n_groups;
   int32_t rb;                       // resolved bits (64 == done)
@@ -88,17 +91,26 @@ constexpr int kHistThreads = 256;
 constexpr int kChunk = 16384;       // elements of one row handled by one CTA (short rows; long rows: chunk_for)
 constexpr int kMaxChunksPerRow = 1024;  // a long row is cut into at most this many chunks: fewer CTAs merging their
                                         // shared histograms into the row's global one (1.25e8-element rows: 7630 -> 954)
-constexpr int kCandCap = 8192;      // candidate list capacity per row (doubles)
-constexpr int kBigBucket = 2048;    // buckets above this are not gathered (resolved by min == max, else by scanning)
+constexpr int kCandCap = 16384;     // candidate list capacity per row (doubles)
+constexpr int kPoolCap = 8192;      // ... of the list the ranks of a multi-GPU call pool (all-reduced: kept small)
+constexpr int kBigBucket = 4096;    // buckets above this are not gathered (resolved by min == max, else by scanning)
 constexpr int kFullPasses = 4;      // passes that may scan the rows before the collect (pass 0 + up to 3 digits);
 constexpr int kFullPassesLong = 5;  // one more digit for rows of more than 2^27 elements (GLOBAL length)
 constexpr int64_t kLongRow = (int64_t)1 << 27;
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 constexpr int kSampleStride = 16;   // adaptive pass 0 reads every 16th chunk of a long row ...
 constexpr int kSampleMinChunks = 8; // ... rows of up to 8 chunks are read whole
-constexpr int kMaxCommonBits = 56;  // the first digit pass always has a digit left to count with
-constexpr int kBelowAt = 256, kAboveAt = 257;  // H slots of the keys outside the sampled prefix (first digit pass)
-constexpr int kBelowZeroAt = 258, kBelowNegAt = 259;  // ... of which: exactly +0.0 / smaller than +0.0 (negative)
+// First digit pass of an adaptive row: kFirstBins equal bins laid over the sampled key range [kmin, kmax] —
+// bin = (key >> s) - (kmin >> s) with the smallest s that fits the range — instead of an 8-bit digit under
+// the common prefix of the two: at least half of the bins are in use whatever the range straddles (a range
+// across a power of two shares almost no leading bits), ~13 bits are resolved by ONE scan, and every bin is
+// still the set of keys with one (64 - s)-bit prefix, so that the following 8-bit passes apply unchanged.
+constexpr int kFirstBins = 8128;
+constexpr int kFirstChunk = 65536;  // elements per CTA of that pass: few CTAs merge 8 K-bin histograms into the row's
+constexpr int kBelowAt = kFirstBins, kAboveAt = kFirstBins + 1;  // H slots of the keys outside the sampled range
+constexpr int kBelowZeroAt = kFirstBins + 2, kBelowNegAt = kFirstBins + 3;  // ... of which: exactly +0.0 / negative
+constexpr int kFirstWords = kFirstBins + 4;
+static_assert(kFirstWords <= kHistWords, "first-digit histogram must fit the row's histogram");
 // The engine pads the yearly series of a failed path with +0.0 (simulation.py:905-912) and clamps final
 // balances at 0, so rows hold a mass of exact zeros next to a bulk of positive balances. Zeros share
 // only the sign bit with the bulk: a common prefix over all keys would be worthless and the zero
@@ -116,7 +128,8 @@ __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ his
   for (int k = threadIdx.x; k < kHistWords; k += blockDim.x) H[k] = 0;
   if (threadIdx.x == 0) {
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
-    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused; R.ready = 0; R.fixed_mask = 0;
+    R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused != 0; R.ready = 0; R.fixed_mask = 0;
+    R.fbase = 0; R.fshift = 64; R.cap = (fused & 2) ? kPoolCap : kCandCap;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
@@ -308,31 +321,47 @@ __device__ __forceinline__ void extremes_elements(const double* __restrict__ x, 
   }
 }
 
-// first digit pass of an adaptive row: digit histogram of the keys that carry the sampled
-// prefix, and the number of keys below / above it
-template <int NT, bool MASKED>
-__device__ __forceinline__ void first_digit_elements(const Probe& P, const double* __restrict__ x,
-                                                     const uint8_t* __restrict__ m, int cnt) {
+// first digit pass of an adaptive row: histogram of the keys over the kFirstBins bins of the sampled
+// range, and the number of keys below / above it. HI32: the bin shift is >= 32 (the usual case — a row
+// whose values spread by more than ~1e-4 relative), so the bin index comes from the key's high word alone.
+template <int NT, bool MASKED, bool HI32>
+__device__ __forceinline__ void first_digit_elements(uint32_t a_hist, uint64_t fbase, int fshift,
+                                                     const double* __restrict__ x, const uint8_t* __restrict__ m,
+                                                     int cnt) {
   const bool lane0 = (threadIdx.x & 31) == 0;
+  const uint32_t base32 = (uint32_t)fbase;       // HI32: fbase = kmin >> fshift fits 32 bits
+  const int sh32 = fshift - 32;
   scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
     int id = -1;
     if (ok) {
-      const uint32_t d_hi = (hi ^ P.p_hi) & P.m_hi, d_lo = (lo ^ P.p_lo) & P.m_lo;
-      const uint64_t k = ((uint64_t)hi << 32) | lo;
-      if ((d_hi | d_lo) == 0u) {
-        id = (int)((uint32_t)(k >> P.dshift) & P.dmask);
-      } else {  // first differing bit decides the side: the key has a 1 where the prefix has a 0 <=> above
-        const uint64_t kp = k & (((uint64_t)P.m_hi << 32) | P.m_lo), pp = ((uint64_t)P.p_hi << 32) | P.p_lo;
-        id = kp > pp ? kAboveAt : kBelowAt;
-        if (id == kBelowAt && k <= kZeroKey)   // zero-padded failures (common), negative keys (rare)
-          red_shared_add(P.a_hist + (uint32_t)(k == kZeroKey ? kBelowZeroAt : kBelowNegAt) * 4u, 1u);
+      bool inside, above;
+      uint32_t bin;
+      if (HI32) {
+        const uint32_t q = hi >> sh32;
+        bin = q - base32;
+        inside = bin < (uint32_t)kFirstBins;
+        above = q > base32;                        // only read when outside
+      } else {
+        const uint64_t q = (((uint64_t)hi << 32) | lo) >> fshift;
+        const uint64_t d = q - fbase;
+        bin = (uint32_t)d;
+        inside = d < (uint64_t)kFirstBins;
+        above = q > fbase;
+      }
+      if (inside) {
+        id = (int)bin;
+      } else {
+        id = above ? kAboveAt : kBelowAt;
+        // zero-padded failures (common), negative keys (rare)
+        if (!above && hi <= 0x80000000u && (hi < 0x80000000u || lo == 0u))
+          red_shared_add(a_hist + (uint32_t)((hi == 0x80000000u && lo == 0u) ? kBelowZeroAt : kBelowNegAt) * 4u, 1u);
       }
     }
     const int id0 = __shfl_sync(0xffffffffu, id, 0);
     if (__all_sync(0xffffffffu, id == id0)) {
-      if (id0 >= 0 && lane0) red_shared_add(P.a_hist + (uint32_t)id0 * 4u, 32u);
+      if (id0 >= 0 && lane0) red_shared_add(a_hist + (uint32_t)id0 * 4u, 32u);
     } else if (id >= 0) {
-      red_shared_add(P.a_hist + (uint32_t)id * 4u, 1u);
+      red_shared_add(a_hist + (uint32_t)id * 4u, 1u);
     }
   });
 }
@@ -373,16 +402,25 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
     if (m) extremes_elements<kHistThreads, true>(x, m, cnt, R); else extremes_elements<kHistThreads, false>(x, m, cnt, R);
     return;
   }
-  const bool first_digit = pass == 1 && R.adaptive && rb > 0;  // counts keys outside the sampled prefix too
+  const int fshift = R.fshift;
+  const bool first_digit = pass == 1 && R.adaptive && fshift < 64;  // counts keys outside the sampled range too
   const int ng = R.n_groups;
-  const int used = first_digit ? 2 * 256 : ng * 256;   // (first digit: 256 bins + below / above / below-other)
+  const int used = first_digit ? kFirstWords : ng * 256;
   for (int k = threadIdx.x; k < used; k += kHistThreads) sh[k] = 0;
-  if (rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
-  const int w = 64 - rb < 8 ? 64 - rb : 8;
-  const Probe P = make_probe(R, rb, w, T, sh);
+  if (!first_digit && rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
   if (first_digit) {
-    if (m) first_digit_elements<kHistThreads, true>(P, x, m, cnt); else first_digit_elements<kHistThreads, false>(P, x, m, cnt);
+    const uint32_t a_hist = smem_addr(sh);
+    const uint64_t fbase = R.fbase;
+    if (fshift >= 32) {
+      if (m) first_digit_elements<kHistThreads, true, true>(a_hist, fbase, fshift, x, m, cnt);
+      else first_digit_elements<kHistThreads, false, true>(a_hist, fbase, fshift, x, m, cnt);
+    } else {
+      if (m) first_digit_elements<kHistThreads, true, false>(a_hist, fbase, fshift, x, m, cnt);
+      else first_digit_elements<kHistThreads, false, false>(a_hist, fbase, fshift, x, m, cnt);
+    }
   } else {
+    const int w = 64 - rb < 8 ? 64 - rb : 8;
+    const Probe P = make_probe(R, rb, w, T, sh);
     hist_dispatch<kHistThreads>(P, x, m, cnt, rb, ng);
   }
   __syncthreads();
@@ -396,20 +434,28 @@ __device__ __forceinline__ void collect_elements(const Probe& P, const double* _
                                                  const uint8_t* __restrict__ m, int cnt, SelRow& R,
                                                  double* __restrict__ out, unsigned long long* s_min,
                                                  unsigned long long* s_max, const int* s_big) {
+  const int cap = R.cap;
+  const unsigned lane = threadIdx.x & 31u;
   scan_elements<kHistThreads, MASKED>(x, m, cnt, [&](bool ok, double v, uint32_t hi, uint32_t lo) {
-    if (!ok) return;
-    const int g = group_of<MODE>(P, hi, lo);
-    if (g < 0) return;
-    // bucket extremes (shared-memory atomics only — no plain read races them —, merged once per
-    // CTA): a bucket of one repeated value is recognised later by min == max. Few elements get
-    // here: the live buckets are small by now, except for repeated values (zero-padded failures).
-    const unsigned long long k = ((unsigned long long)hi << 32) | lo;
-    atomicMin(&s_min[g], k);
-    atomicMax(&s_max[g], k);
-    if (!s_big[g]) {
-      // an overflowing list is detected from n_cand by k_sel_collect_finish
-      const int at = atomicAdd(&R.n_cand, 1);
-      if (at < kCandCap) out[at] = v;
+    const int g = ok ? group_of<MODE>(P, hi, lo) : -1;
+    bool take = false;
+    if (g >= 0) {
+      // bucket extremes (shared-memory atomics only — no plain read races them —, merged once per
+      // CTA): a bucket of one repeated value is recognised later by min == max. Few elements get
+      // here: the live buckets are small by now, except for repeated values (zero-padded failures).
+      const unsigned long long k = ((unsigned long long)hi << 32) | lo;
+      atomicMin(&s_min[g], k);
+      atomicMax(&s_max[g], k);
+      take = !s_big[g];
+    }
+    // one list-cursor atomic per warp; an overflowing list is detected from n_cand by k_sel_collect_finish
+    const unsigned takers = __ballot_sync(0xffffffffu, take);
+    if (takers) {
+      const int leader = __ffs(takers) - 1;
+      int at = 0;
+      if ((int)lane == leader) at = atomicAdd(&R.n_cand, __popc(takers));
+      at = __shfl_sync(0xffffffffu, at, leader) + __popc(takers & ((1u << lane) - 1u));
+      if (take && at < cap) out[at] = v;
     }
   });
 }
@@ -473,7 +519,7 @@ __global__ void k_sel_extremes(SelRow* __restrict__ rows, long long* __restrict_
 __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   SelRow& R = rows[blockIdx.x];
   if (threadIdx.x == 0 && R.rb < 64 && !R.collected) {
-    if (R.n_cand > kCandCap) { R.n_cand = kCandCap; R.overflow = 1; }
+    if (R.n_cand > R.cap) { R.n_cand = R.cap; R.overflow = 1; }
     // stepwise (multi-GPU) protocol: later passes histogram the list, so a row with a bucket
     // that was not gathered keeps scanning the full row instead
     if (!R.fused)
@@ -526,11 +572,11 @@ __device__ void set_target_ranks(SelRow& R, int64_t nv) {
 
 // One pass, second half (one warp per target + housekeeping): consume the merged histogram H
 // of row R. Needs >= 32 * (2 * n_q) threads; ends with H cleared and the next pass's groups set.
-//   adaptive rows:  pass 0 took (sampled) extreme keys -> the common prefix, nothing counted yet;
-//                   pass 1 histogrammed the first digit below that prefix, plus the keys outside
-//                   it -> valid count, target ranks, first walk. A target that falls outside the
-//                   sampled prefix (only possible if the sample missed that much of the row)
-//                   restarts the row from bit 0 as a non-adaptive one;
+//   adaptive rows:  pass 0 took (sampled) extreme keys -> the bin window of the first digit pass, nothing
+//                   counted yet; pass 1 histogrammed the kFirstBins bins of that window, plus the keys
+//                   outside it -> valid count, target ranks, first walk (64 - fshift bits resolved). A
+//                   target that falls outside the window (only possible if the sample missed that
+//                   much of the row) restarts the row from bit 0 as a non-adaptive one;
 //   other rows:     pass 0 histogrammed the top digit -> valid count, target ranks, first walk.
 __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   __shared__ int s_restart;
@@ -541,7 +587,8 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   const int rb = R.rb;
   const bool adaptive = R.adaptive != 0;
   const bool extremes_only = adaptive && pass == 0;
-  const bool first_digit = adaptive && pass == 1 && rb > 0;       // below / above slots are live
+  const int fshift = R.fshift;
+  const bool first_digit = adaptive && pass == 1 && fshift < 64;  // window bins; below / above slots are live
   const bool counts_now = adaptive ? pass == 1 : pass == 0;       // this histogram carries the valid count
   if (tid == 0) s_restart = 0;
   __syncthreads();
@@ -549,7 +596,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
     if (counts_now) {
       if (warp == 0) {
         int64_t part = 0;
-        for (int d = lane; d < 256; d += 32) part += H[d];
+        for (int d = lane; d < (first_digit ? kFirstBins : 256); d += 32) part += H[d];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
@@ -596,59 +643,81 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
     }
     const bool all_fixed = s_restart == 2;
     const bool restart = s_restart == 1;
-    // warp t walks target t's bucket histogram (8 bins per lane + warp scan) to the digit
-    // holding its rank
+    // warp t walks target t's bucket histogram (8 bins per lane + warp scan, 256 bins at a time) to
+    // the bin holding its rank
     const int w = 64 - rb < 8 ? 64 - rb : 8;
     if (!extremes_only && !restart && !all_fixed && warp < nt && R.n_valid > 0) {
-      const uint32_t* h = H + R.group[warp] * 256;
-      uint32_t c[8];
-      uint32_t local = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; local += c[k]; }
-      uint32_t incl = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-      }
+      const uint32_t* h = first_digit ? H : H + R.group[warp] * 256;
+      const int nb = first_digit ? kFirstBins : 256;
       const int64_t r = R.rank[warp];
-      const int64_t before = (int64_t)incl - local;
-      const bool mine = r >= before && r < (int64_t)incl;
-      const unsigned who = __ballot_sync(0xffffffffu, mine);
-      if (who == 0) {  // rank beyond the bucket (cannot happen for consistent histograms): last bin
-        if (lane == 31) { R.rank[warp] = 0; R.bcount[warp] = 0; R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)((1u << w) - 1u); }
-      } else if (lane == __ffs(who) - 1) {
-        int64_t rr = r - before;
-        int k = 0;
-        for (; k < 7; ++k) {
-          if (rr < (int64_t)c[k]) break;
-          rr -= c[k];
+      int64_t running = 0;
+      bool found = false;
+      for (int blk = 0; blk < nb && !found; blk += 256) {
+        uint32_t c[8];
+        uint32_t local = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int b = blk + lane * 8 + k;
+          c[k] = b < nb ? h[b] : 0u;
+          local += c[k];
         }
-        R.rank[warp] = rr;
-        R.bcount[warp] = c[k];
-        R.prefix[warp] = (R.prefix[warp] << w) | (uint64_t)(lane * 8 + k);
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const int64_t before = running + (int64_t)incl - local;
+        const bool mine = r >= before && r < running + (int64_t)incl;
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        running += (int64_t)__shfl_sync(0xffffffffu, incl, 31);
+        if (who == 0) continue;
+        found = true;
+        if (lane == __ffs(who) - 1) {
+          int64_t rr = r - before;
+          int k = 0;
+          for (; k < 7; ++k) {
+            if (rr < (int64_t)c[k]) break;
+            rr -= c[k];
+          }
+          R.rank[warp] = rr;
+          R.bcount[warp] = c[k];
+          const uint64_t bin = (uint64_t)(blk + lane * 8 + k);
+          R.prefix[warp] = first_digit ? R.fbase + bin : ((R.prefix[warp] << w) | bin);
+        }
+      }
+      if (!found && lane == 31) {  // rank beyond the bucket (cannot happen for consistent histograms): last bin
+        R.rank[warp] = 0;
+        R.bcount[warp] = 0;
+        R.prefix[warp] = first_digit ? R.fbase + (uint64_t)(kFirstBins - 1) : ((R.prefix[warp] << w) | (uint64_t)((1u << w) - 1u));
       }
     }
     __syncthreads();
     if (tid == 0) {
-      int nrb = rb + w;
+      int nrb = first_digit ? 64 - fshift : rb + w;
       bool counted = true;
       if (extremes_only) {
-        // the keys seen share the leading clz(kmin ^ kmax) bits: resolved for free (at most
-        // kMaxCommonBits, so that the next pass still has a digit to count the row with).
-        // Nothing seen (empty / all-NaN sample): start from bit 0.
-        const uint64_t x = R.kmin ^ R.kmax;
-        int c = R.kmin > R.kmax ? 0 : (x ? __clzll((long long)x) : 64);
-        c = c > kMaxCommonBits ? kMaxCommonBits : c;
-        nrb = c;
+        // the window of the first digit pass: the smallest bin width 2^s that lays at most kFirstBins
+        // bins over [kmin, kmax]. Nothing seen (empty / all-NaN / all-zero sample): no window, the next
+        // pass histograms the top digit from bit 0.
+        nrb = 0;
+        if (R.kmin <= R.kmax) {
+          int sft = 0;
+          while (((R.kmax >> sft) - (R.kmin >> sft)) >= (uint64_t)kFirstBins) ++sft;
+          R.fshift = sft;
+          R.fbase = R.kmin >> sft;
+        } else {
+          R.fshift = 64;
+        }
         for (int t = 0; t < nt; ++t) {
-          R.prefix[t] = c == 0 ? 0ull : (R.kmin >> (64 - c));
+          R.prefix[t] = 0ull;
           R.bcount[t] = 0;
         }
         counted = false;
       } else if (restart) {
         nrb = 0;
         R.adaptive = 0;
+        R.fshift = 64;
       } else if (R.n_valid <= 0 || all_fixed) {
         nrb = 64;
       }
@@ -671,7 +740,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
       // repeated value — zero-padded failed paths — never shrinks)
       // (only where a tail kernel finishes the row from the gathered list: the plain stepwise
       // protocol keeps histogramming, so it has no use for an early stop)
-      const bool ready = counted && !restart && R.fused && nrb < 64 && total <= kCandCap;
+      const bool ready = counted && !restart && R.fused && nrb < 64 && total <= R.cap;
       for (int k = 0; k < g; ++k) R.gbig[k] = (!ready && (!counted || restart || gcount[k] > kBigBucket)) ? 1 : 0;
       R.ready = ready ? 1 : 0;
     }
@@ -707,93 +776,62 @@ __device__ __forceinline__ double finish_value(const SelRow& R, int k) {
 }
 
 // Single-GPU tail: whatever is left of a row after the collect, in ONE launch, followed by the
-// interpolation. Candidate lists are bitonic-sorted in shared memory and every target is read
-// off the sorted list; an overflowed bucket of one repeated value is resolved by its extremes;
-// an overflowed bucket of distinct values scans the full row here (slow, rare).
+// interpolation: the remaining 8-bit digits are walked by this CTA alone, histogram in shared memory —
+// over the gathered candidate list (L2-resident, at most kCandCap elements: every live bucket is either in
+// it or one repeated value known from its extremes), or, when a bucket of distinct values overflowed the
+// list, over the full row (slow, rare).
 constexpr int kTailThreads = 1024;
 __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ rows, const double* __restrict__ cand,
-                                                           double* __restrict__ out, int out_stride,
+                                                           int cand_stride, double* __restrict__ out, int out_stride,
                                                            int64_t* __restrict__ counts,
                                                            long long* __restrict__ unresolved) {
-  extern __shared__ uint64_t s_keys[];  // kCandCap keys (64 KB), reused as the histogram on the slow path
+  extern __shared__ uint32_t s_hist[];  // [kHistWords]
   __shared__ PrefixTable T;
   __shared__ int need_scan;
+  __shared__ int s_one[kMaxTargets];         // target sits in an ungathered bucket of one repeated value ...
+  __shared__ uint64_t s_one_key[kMaxTargets];  // ... this one
   SelRow& R = rows[blockIdx.x];
   const QuantileSpec& spec = R.d.spec;
-  const int64_t n = R.d.n;
-  const uint8_t* __restrict__ mask = R.d.mask;
   const int tid = threadIdx.x;
   const int nt = 2 * spec.n_q;
-  const int rb = R.rb;
-  if (rb < 64 && R.n_valid > 0) {
+  if (R.rb < 64 && R.n_valid > 0) {
     // which targets can be read off the gathered list / off a one-value bucket, and is a scan needed?
     if (tid == 0) need_scan = 0;
     __syncthreads();
     if (tid < nt) {
       const int g = R.group[tid];
+      s_one[tid] = R.gbig[g];
+      s_one_key[tid] = R.gmin[g];
       if (R.gbig[g] ? (R.gmin[g] != R.gmax[g]) : (R.overflow != 0)) atomicOr(&need_scan, 1);
     }
     __syncthreads();
-    if (!need_scan) {
-      const int nc = R.n_cand;
-      int m = 32;
-      while (m < nc) m <<= 1;
-      const double* __restrict__ c = cand + (size_t)blockIdx.x * kCandCap;
-      for (int i = tid; i < m; i += kTailThreads) s_keys[i] = i < nc ? key_of(c[i]) : ~0ull;
-      __syncthreads();
-      for (int k = 2; k <= m; k <<= 1) {          // bitonic sort, ascending
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = tid; i < m; i += kTailThreads) {
-            const int ixj = i ^ j;
-            if (ixj > i) {
-              const uint64_t a = s_keys[i], b = s_keys[ixj];
-              const bool up = (i & k) == 0;
-              if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
-            }
-          }
-          __syncthreads();
-        }
-      }
-      if (tid < nt) {
-        const int g = R.group[tid];
-        if (R.gbig[g]) {
-          R.prefix[tid] = R.gmin[g];            // a bucket of one repeated value
-        } else {
-          // candidates of this target = keys sharing its resolved prefix; they are contiguous
-          // in the sorted list and its residual rank counts from the first of them
-          const uint64_t lo_key = rb == 0 ? 0ull : (R.prefix[tid] << (64 - rb));
-          int lo = 0, hi = nc;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_keys[mid] < lo_key) lo = mid + 1; else hi = mid;
-          }
-          const int64_t at = lo + R.rank[tid];
-          R.prefix[tid] = s_keys[at < nc ? at : nc - 1];
-        }
-      }
-      __syncthreads();
-    } else if (unresolved) {
+    if (need_scan && unresolved) {
       // path shards on several GPUs: this rank only holds part of the row, so the row cannot be
       // finished by scanning here — report it (the caller re-runs the stepwise protocol)
       if (tid == 0) atomicAdd((unsigned long long*)unresolved, 1ull);
     } else {
-      uint32_t* sh = (uint32_t*)s_keys;
-      const double* __restrict__ x = R.d.x;
+      const bool from_list = !need_scan;
+      const double* __restrict__ x = from_list ? cand + (size_t)blockIdx.x * cand_stride : R.d.x;
+      const uint8_t* __restrict__ mask = from_list ? nullptr : R.d.mask;
+      const int64_t n = from_list ? (int64_t)R.n_cand : R.d.n;
       if (tid == 0) { R.ready = 0; R.fused = 0; }  // no early stop from here on: every digit is walked
       __syncthreads();
-      for (int pass = kFullPasses; R.rb < 64; ++pass) {
+      for (int pass = kFullPassesLong; R.rb < 64; ++pass) {
         const int cur = R.rb, ng = R.n_groups;
         const int w = 64 - cur < 8 ? 64 - cur : 8;
-        for (int k = tid; k < kHistWords; k += kTailThreads) sh[k] = 0;
+        for (int k = tid; k < ng * 256; k += kTailThreads) s_hist[k] = 0;
         if (cur > 0 && ng > 1) build_table(T, R, ng, cur); else __syncthreads();
-        const Probe P = make_probe(R, cur, w, T, sh);
+        const Probe P = make_probe(R, cur, w, T, s_hist);
         for (int64_t b0 = 0; b0 < n; b0 += (1 << 30)) {
           const int cnt = (int)(n - b0 < (1 << 30) ? n - b0 : (1 << 30));
           hist_dispatch<kTailThreads>(P, x + b0, mask ? mask + b0 : nullptr, cnt, cur, ng);
         }
         __syncthreads();
-        advance_row(R, sh, pass);
+        advance_row(R, s_hist, pass);
       }
+      // (a one-value bucket is not in the list: its targets walked empty histograms above)
+      if (from_list && tid < nt && s_one[tid]) R.prefix[tid] = s_one_key[tid];
+      __syncthreads();
     }
   }
   if (tid < spec.n_q) out[(int64_t)blockIdx.x * out_stride + tid] = finish_value(R, tid);
@@ -805,7 +843,7 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
 // small by then (the rows stopped scanning because the GLOBAL histogram said they fit the
 // list), so instead of more all-reduced digit passes the ranks pool the candidates and each
 // finishes every row with the single-GPU tail. The exchange buffer is one int64 array
-//   xbuf = [ unresolved | counts[world][rows] | group extremes[rows][kMaxTargets][2] | pool[rows][kCandCap] ]
+//   xbuf = [ unresolved | counts[world][rows] | group extremes[rows][kMaxTargets][2] | pool[rows][kPoolCap] ]
 // whose regions are combined by plain all-reduces: SUM of the counts (each rank fills only its
 // own line), MIN of the encoded extremes (as k_sel_extremes), SUM of the pool (each rank writes
 // its candidates, as bit patterns, at its own offset into zeros).
@@ -822,7 +860,7 @@ __global__ void k_sel_export(SelRow* __restrict__ rows, long long* __restrict__ 
   if (r == 0 && threadIdx.x == 0) xbuf[0] = 0;
   for (int q = threadIdx.x; q < world; q += blockDim.x) {
     long long c = 0;
-    if (q == rank && R.rb < 64) c = R.overflow ? (long long)kCandCap + 1 : (long long)R.n_cand;
+    if (q == rank && R.rb < 64) c = R.overflow ? (long long)kPoolCap + 1 : (long long)R.n_cand;
     xbuf[xbuf_counts_at() + (size_t)q * n_rows + r] = c;
   }
   long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * kMaxTargets * 2;
@@ -851,8 +889,8 @@ __global__ void k_sel_place(SelRow* __restrict__ rows, const double* __restrict_
   __syncthreads();
   const long long total = s_total, off = s_off;
   const int mine = R.n_cand;
-  long long* pool = xbuf + xbuf_pool_at(n_rows, world) + (size_t)r * kCandCap;
-  if (total <= kCandCap) {
+  long long* pool = xbuf + xbuf_pool_at(n_rows, world) + (size_t)r * kPoolCap;
+  if (total <= kPoolCap) {
     const double* __restrict__ c = cand + (size_t)r * kCandCap;
     for (int i = threadIdx.x; i < mine; i += blockDim.x) pool[off + i] = __double_as_longlong(c[i]);
   }
@@ -863,8 +901,8 @@ __global__ void k_sel_place(SelRow* __restrict__ rows, const double* __restrict_
     R.gmax[threadIdx.x] = ~((unsigned long long)e[2 * threadIdx.x + 1] ^ top);
   }
   if (threadIdx.x == 0) {
-    R.overflow = total > kCandCap ? 1 : 0;
-    R.n_cand = total > kCandCap ? kCandCap : (int)total;
+    R.overflow = total > kPoolCap ? 1 : 0;
+    R.n_cand = total > kPoolCap ? kPoolCap : (int)total;
   }
 }
 
@@ -1024,18 +1062,13 @@ size_t quantile_state_bytes(int rows) {
 }
 size_t quantile_hist_bytes(int rows) { return sizeof(uint32_t) * kHistWords * (size_t)(rows > 0 ? rows : 1); }
 static double* cand_of(void* state, int rows) { return (double*)((char*)state + sizeof(SelRow) * (size_t)rows); }
-static RowDesc* desc_of(void* state, int rows) {
+RowDesc* select_desc_area(void* state, int rows) {
   return (RowDesc*)((char*)state + (sizeof(SelRow) + sizeof(double) * kCandCap) * (size_t)rows);
 }
 
-cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, void* hist, cudaStream_t st, int adaptive,
-                             int fused) {
+cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive, int fused) {
   if (rows <= 0) return cudaSuccess;
-  // pageable source: staged before the call returns
-  cudaError_t e = cudaMemcpyAsync(desc_of(state, rows), desc_host, sizeof(RowDesc) * (size_t)rows,
-                                  cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return e;
-  k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist, desc_of(state, rows), adaptive, fused);
+  k_sel_init<<<rows, 256, 0, st>>>((SelRow*)state, (uint32_t*)hist, select_desc_area(state, rows), adaptive, fused);
   return cudaGetLastError();
 }
 
@@ -1051,6 +1084,7 @@ static int chunk_for(int64_t max_n) {
 cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st, int sampled) {
   if (rows <= 0 || max_n <= 0) return cudaSuccess;
   int chunk = chunk_for(max_n), stride = 1;
+  if (pass == 1 && chunk < kFirstChunk) chunk = kFirstChunk;   // the (wide) first digit pass of adaptive rows
   unsigned grid = (unsigned)((max_n + chunk - 1) / chunk);
   if (pass == 0) {
     // adaptive calls only sample the rows for their extreme keys in pass 0: ~64 pieces of 16 K
@@ -1113,7 +1147,7 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
     max_n = desc_host[r].n > max_n ? desc_host[r].n : max_n;
     max_nq = desc_host[r].spec.n_q > max_nq ? desc_host[r].spec.n_q : max_nq;
   }
-  cudaError_t e = launch_sel_begin(rows, desc_host, state, hist, st, /*adaptive=*/1, /*fused=*/1);
+  cudaError_t e = launch_sel_begin(rows, state, hist, st, /*adaptive=*/1, /*fused=*/1);
   ++*n_launches;
   const int full = select_full_passes_for(max_n);
   for (int pass = 0; pass < full && e == cudaSuccess; ++pass) {
@@ -1126,10 +1160,8 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
   *n_launches += 1 + (max_n > 0);
   if (e != cudaSuccess) return e;
   // one launch for the remaining digits + interpolation (see k_sel_tail)
-  e = cudaFuncSetAttribute(k_sel_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * kCandCap));
-  if (e != cudaSuccess) return e;
-  k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>((SelRow*)state, cand_of(state, rows), out,
-                                                                      out_stride, counts, nullptr);
+  k_sel_tail<<<rows, kTailThreads, sizeof(uint32_t) * kHistWords, st>>>((SelRow*)state, cand_of(state, rows), kCandCap, out,
+                                                                        out_stride, counts, nullptr);
   ++*n_launches;
   return cudaGetLastError();
 }
@@ -1140,7 +1172,7 @@ int select_full_passes_for(int64_t n_global_max) { return n_global_max > kLongRo
 size_t select_exchange_words(int rows, int world) {
   rows = rows > 0 ? rows : 1;
   world = world > 0 ? world : 1;
-  return xbuf_pool_at(rows, world) + (size_t)rows * kCandCap;
+  return xbuf_pool_at(rows, world) + (size_t)rows * kPoolCap;
 }
 void select_exchange_layout(int rows, int world, int64_t at[4]) {
   at[0] = (int64_t)xbuf_counts_at();
@@ -1151,7 +1183,7 @@ void select_exchange_layout(int rows, int world, int64_t at[4]) {
 
 cudaError_t launch_sel_export(int rows, void* state, long long* xbuf, int rank, int world, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(xbuf + xbuf_pool_at(rows, world), 0, sizeof(long long) * (size_t)rows * kCandCap, st);
+  cudaError_t e = cudaMemsetAsync(xbuf + xbuf_pool_at(rows, world), 0, sizeof(long long) * (size_t)rows * kPoolCap, st);
   if (e != cudaSuccess) return e;
   k_sel_export<<<rows, 64, 0, st>>>((SelRow*)state, xbuf, rows, rank, world);
   return cudaGetLastError();
@@ -1165,10 +1197,8 @@ cudaError_t launch_sel_place(int rows, void* state, long long* xbuf, int rank, i
 cudaError_t launch_sel_tail_pooled(int rows, void* state, long long* xbuf, int world, double* out, int out_stride,
                                    int64_t* counts, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_sel_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint64_t) * kCandCap));
-  if (e != cudaSuccess) return e;
-  k_sel_tail<<<rows, kTailThreads, sizeof(uint64_t) * kCandCap, st>>>(
-      (SelRow*)state, (const double*)(xbuf + xbuf_pool_at(rows, world)), out, out_stride, counts, xbuf);
+  k_sel_tail<<<rows, kTailThreads, sizeof(uint32_t) * kHistWords, st>>>(
+      (SelRow*)state, (const double*)(xbuf + xbuf_pool_at(rows, world)), kPoolCap, out, out_stride, counts, xbuf);
   return cudaGetLastError();
 }
 

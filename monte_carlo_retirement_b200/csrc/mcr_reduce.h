@@ -23,12 +23,15 @@ struct RowDesc {
   QuantileSpec spec;
 };
 
-// all rows in ONE launch sequence (rows may differ in source, length, mask and quantiles)
+// Where a select call expects its rows' descriptors: the caller copies RowDesc[rows] there (on the call's
+// stream) before launch_quantiles_rows / launch_sel_begin.
+RowDesc* select_desc_area(void* state, int rows);
+// all rows in ONE launch sequence (rows may differ in source, length, mask and quantiles); desc_host only
+// sizes the grids here
 cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* out, int out_stride, int64_t* counts,
                                   void* state, void* hist, cudaStream_t st, int* n_launches);
 // the same select, one pass at a time (a multi-GPU caller all-reduces `hist` between hist and advance)
-cudaError_t launch_sel_begin(int rows, const RowDesc* desc_host, void* state, void* hist, cudaStream_t st,
-                             int adaptive = 0, int fused = 0);
+cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive = 0, int fused = 0);
 cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st,
                             int sampled = 0);
 cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st);

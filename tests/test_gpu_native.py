@@ -281,6 +281,45 @@ def test_quantiles_of_long_rows_are_exact_whatever_the_sampled_extremes_miss():
     sim.native_context.quantiles(_dev(x[0]), n, n, 1, [0.5], med, median=True, mask=_dev(mask))   # masked-out sample
     assert med.item() == np.median(x[0][~sampled])
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [5_000, 1_000_000])
+def test_quantiles_whatever_the_first_digit_window_looks_like(n):
+    """The first digit pass lays ~8 K equal bins over the (sampled) key range of a row: ranges
+    narrower than the low 32 key bits, ranges across a power of two, ranges stretched by outliers so
+    far that the bulk stays in one bucket through every full pass (the tail then scans the row),
+    buckets of a few distinct values, sign changes. Bit for bit against pandas."""
+    import torch
+
+    rng = np.random.default_rng(n + 17)
+    u = rng.random(n)
+    rows = [
+        1.0 + u * 1e-12,                                   # 0: ~4500 distinct keys, all in the low key bits
+        1.0 + u * 1e-7,                                    # 1: bin shift < 32
+        1048576.0 * (0.999 + 0.002 * u),                   # 2: across 2^20 (no common leading bits to speak of)
+        np.where(u < 0.5, -1e-300, 1e-300) * (1 + rng.random(n)),   # 3: across zero, nothing near it
+        np.concatenate([[1e-200, 1e200], 1.0 + rng.random(n - 2) * 1e-9]),   # 4: bulk in one bucket of distinct values
+        np.round(rng.normal(0, 3, n)),                     # 5: ~20 distinct values, negative to positive, with -0/+0
+        rng.standard_cauchy(n) * 1e6,                      # 6: heavy tails on both sides
+        np.exp(rng.normal(14, 1.0, n)),                    # 7: the ordinary band row
+        np.full(n, -3.5),                                  # 8: constant, negative
+        np.where(u < 0.9, 2.0, 2.0 + 4.4e-16),             # 9: two adjacent keys
+    ]
+    x = np.stack(rows)
+    q = [0.0, 0.05, 0.10, 0.25, 0.50, 0.75, 0.90, 0.95, 1.0]
+    sim = make_sim(scenarios.TEST_BASE)
+    out = torch.empty((len(rows), len(q)), dtype=torch.float64, device="cuda")
+    cnt = torch.empty(len(rows), dtype=torch.int64, device="cuda")
+    sim.native_context.quantiles(_dev(x), n, n, len(rows), q, out, counts=cnt)
+    want = pd.DataFrame(x.T).quantile(q, axis=0).T.to_numpy()
+    got = out.cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True), np.argwhere(got != want)
+    assert cnt.cpu().tolist() == [n] * len(rows)
+    mask = rng.random(n) < 0.5
+    med = torch.empty((len(rows), 1), dtype=torch.float64, device="cuda")
+    sim.native_context.quantiles(_dev(x), n, n, len(rows), [0.5], med, mask=_dev(mask, np.uint8), median=True)
+    want_med = np.array([np.median(r[mask]) for r in x])
+    assert np.array_equal(med.cpu().numpy()[:, 0], want_med)
+
 
 def test_histograms_match_numpy_and_frontend_rule():
     import torch
