@@ -250,6 +250,8 @@ int mcr_sweep_batch(mcr_ctx* ctx, int seed_stream, const mcr_params* scenarios_h
 #define MCR_SEL_MEDIAN 0x1u /* np.median rule: mean of the two middle order statistics
                                (Series.median at simulation.py:96, server.py:449-450);
                                q_host is ignored and n_q results per row are all the median */
+#define MCR_SEL_MINMAX 0x2u /* the row's minimum and maximum over the valid elements: n_q must be 2, q ignored;
+                              * out[0] = min, out[1] = max (NaN for an empty row) — exact elements, no lerp */
 
 /* Exact order-statistic quantiles of `rows` rows of `n` doubles each (values_dev + r * ld) with
  * numpy's 'linear' interpolation, replacing DataFrame.quantile(q, axis=1) at
@@ -275,7 +277,7 @@ typedef struct mcr_select_row {
   const uint8_t* mask_dev;
   int64_t n;
   int32_t n_q;
-  uint32_t flags; /* MCR_SEL_MEDIAN */
+  uint32_t flags; /* MCR_SEL_MEDIAN | MCR_SEL_MINMAX */
   double q[MCR_MAX_QUANTILES];
 } mcr_select_row;
 

@@ -29,6 +29,10 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
 if os.environ.get("MCR_MIN_BLOCKS"):  # tuning experiments only
     COMMON += [f"-DMCR_MIN_BLOCKS={int(os.environ['MCR_MIN_BLOCKS'])}"]
+if os.environ.get("MCR_SCAN_UNROLL"):
+    COMMON += [f"-DMCR_SCAN_UNROLL={int(os.environ['MCR_SCAN_UNROLL'])}"]
+if os.environ.get("MCR_FIRST_CHUNK"):
+    COMMON += [f"-DMCR_FIRST_CHUNK={int(os.environ['MCR_FIRST_CHUNK'])}"]
 if os.environ.get("MCR_BLOCK"):
     COMMON += [f"-DMCR_BLOCK={int(os.environ['MCR_BLOCK'])}"]
 UNITS = [

@@ -586,9 +586,10 @@ static int make_spec(mcr_ctx* ctx, const double* q_host, int32_t n_q, uint32_t s
   if (n_q <= 0 || n_q > kMaxQuantiles) return fail(ctx, MCR_EINVAL, "n_q must be in [1,16]");
   std::memset(&spec, 0, sizeof(spec));
   spec.n_q = n_q;
-  spec.median = (sel_flags & MCR_SEL_MEDIAN) ? 1 : 0;
+  spec.median = (sel_flags & MCR_SEL_MEDIAN) ? 1 : ((sel_flags & MCR_SEL_MINMAX) ? 2 : 0);
+  if (spec.median == 2 && n_q != 2) return fail(ctx, MCR_EINVAL, "MCR_SEL_MINMAX needs n_q == 2");
   for (int k = 0; k < n_q; ++k) {
-    spec.q[k] = spec.median ? 0.5 : (q_host ? q_host[k] : -1.0);
+    spec.q[k] = spec.median == 1 ? 0.5 : (spec.median == 2 ? (double)k : (q_host ? q_host[k] : -1.0));
     if (!(spec.q[k] >= 0.0 && spec.q[k] <= 1.0)) return fail(ctx, MCR_EINVAL, "quantiles must be in [0,1]");
     if (k > 0 && spec.q[k] < spec.q[k - 1]) return fail(ctx, MCR_EINVAL, "quantiles must be ascending");
   }

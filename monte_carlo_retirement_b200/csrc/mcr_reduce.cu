@@ -20,6 +20,13 @@
 
 #include "mcr_reduce.h"
 
+#ifndef MCR_SCAN_UNROLL
+#define MCR_SCAN_UNROLL 4
+#endif
+#ifndef MCR_FIRST_CHUNK
+#define MCR_FIRST_CHUNK 32768
+#endif
+
 namespace mcr {
 
 namespace {
@@ -72,10 +79,12 @@ struct SelRow {
   int32_t slot[kMaxTargets];        // (quantile, lo/hi) -> rank-sorted target slot
   uint64_t kmin, kmax;              // row extremes over the keys != +0.0 (pass 0, adaptive mode)
   uint64_t fbase;                   // first digit pass of an adaptive row: bin = (key >> fshift) - fbase
-  uint32_t fixed_mask;              // targets resolved to +0.0 by the first digit pass (see advance_row)
+  uint64_t omin, omax;              // extreme keys seen OUTSIDE the window by the first digit pass (this GPU's elements)
+  uint64_t fixed_key[kMaxTargets];  // per target of fixed_mask: its key
+  uint32_t fixed_mask;              // targets resolved by the first digit pass itself (see advance_row)
   int32_t fshift;                   //   (64: no window — nothing sampled, or the row restarted from bit 0)
   int32_t cap;                      // candidate list capacity of this call (kCandCap; kPoolCap when ranks pool lists)
-  int32_t pad0;
+  int32_t whole;                    // the row is complete on this GPU (single-GPU call): omin / omax are the row's
   int64_t n_valid;
   int32_t n_groups;
   int32_t rb;                       // resolved bits (64 == done)
@@ -106,10 +115,12 @@ constexpr int kSampleMinChunks = 8; // ... rows of up to 8 chunks are read whole
 // across a power of two shares almost no leading bits), ~13 bits are resolved by ONE scan, and every bin is
 // still the set of keys with one (64 - s)-bit prefix, so that the following 8-bit passes apply unchanged.
 constexpr int kFirstBins = 8128;
-constexpr int kFirstChunk = 65536;  // elements per CTA of that pass: few CTAs merge 8 K-bin histograms into the row's
+constexpr int kFirstChunk = MCR_FIRST_CHUNK;  // elements per CTA of that pass: few CTAs merge 8 K-bin histograms into the row's
 constexpr int kBelowAt = kFirstBins, kAboveAt = kFirstBins + 1;  // H slots of the keys outside the sampled range
 constexpr int kBelowZeroAt = kFirstBins + 2, kBelowNegAt = kFirstBins + 3;  // ... of which: exactly +0.0 / negative
 constexpr int kFirstWords = kFirstBins + 4;
+constexpr int kFirstBlocks = (kFirstBins + 255) / 256;   // 256-bin blocks of the window histogram (<= 32)
+static_assert(kFirstBlocks <= 32, "one lane per block in advance_row");
 static_assert(kFirstWords <= kHistWords, "first-digit histogram must fit the row's histogram");
 // The engine pads the yearly series of a failed path with +0.0 (simulation.py:905-912) and clamps final
 // balances at 0, so rows hold a mass of exact zeros next to a bulk of positive balances. Zeros share
@@ -130,6 +141,7 @@ __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ his
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
     R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused != 0; R.ready = 0; R.fixed_mask = 0;
     R.fbase = 0; R.fshift = 64; R.cap = (fused & 2) ? kPoolCap : kCandCap;
+    R.omin = ~0ull; R.omax = 0ull; R.whole = fused == 1;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
@@ -148,6 +160,15 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
 }
 __device__ __forceinline__ void lds_u64(uint32_t a, uint32_t& lo, uint32_t& hi) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+// red.shared.add under a predicate: one predicated instruction, no branch / reconvergence pair around it
+__device__ __forceinline__ void red_shared_add_if(bool p, uint32_t a, uint32_t v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
 }
 __device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -230,7 +251,7 @@ __device__ __forceinline__ int group_of(const Probe& P, uint32_t hi, uint32_t lo
 template <int NT, bool MASKED, typename Body>
 __device__ __forceinline__ void scan_elements(const double* __restrict__ x, const uint8_t* __restrict__ m, int cnt,
                                               Body body) {
-  constexpr int U = 4;  // independent loads in flight per thread
+  constexpr int U = MCR_SCAN_UNROLL;  // independent loads in flight per thread
   const int tid = threadIdx.x;
   int base = 0;
   for (; base + U * NT <= cnt; base += U * NT) {  // full tiles: no bounds checks
@@ -327,41 +348,53 @@ __device__ __forceinline__ void extremes_elements(const double* __restrict__ x, 
 template <int NT, bool MASKED, bool HI32>
 __device__ __forceinline__ void first_digit_elements(uint32_t a_hist, uint64_t fbase, int fshift,
                                                      const double* __restrict__ x, const uint8_t* __restrict__ m,
-                                                     int cnt) {
+                                                     int cnt, unsigned long long* s_out) {
   const bool lane0 = (threadIdx.x & 31) == 0;
   const uint32_t base32 = (uint32_t)fbase;       // HI32: fbase = kmin >> fshift fits 32 bits
   const int sh32 = fshift - 32;
+  // the hot path is branch-free: bin index, one predicated shared-memory atomic, one vote
   scan_elements<NT, MASKED>(x, m, cnt, [&](bool ok, double, uint32_t hi, uint32_t lo) {
-    int id = -1;
-    if (ok) {
-      bool inside, above;
-      uint32_t bin;
-      if (HI32) {
-        const uint32_t q = hi >> sh32;
-        bin = q - base32;
-        inside = bin < (uint32_t)kFirstBins;
-        above = q > base32;                        // only read when outside
-      } else {
-        const uint64_t q = (((uint64_t)hi << 32) | lo) >> fshift;
-        const uint64_t d = q - fbase;
-        bin = (uint32_t)d;
-        inside = d < (uint64_t)kFirstBins;
-        above = q > fbase;
-      }
-      if (inside) {
-        id = (int)bin;
-      } else {
-        id = above ? kAboveAt : kBelowAt;
-        // zero-padded failures (common), negative keys (rare)
-        if (!above && hi <= 0x80000000u && (hi < 0x80000000u || lo == 0u))
-          red_shared_add(a_hist + (uint32_t)((hi == 0x80000000u && lo == 0u) ? kBelowZeroAt : kBelowNegAt) * 4u, 1u);
-      }
+    uint32_t bin;
+    bool above;
+    if (HI32) {
+      const uint32_t q = hi >> sh32;
+      bin = q - base32;
+      above = q > base32;                          // only read when outside
+    } else {
+      const uint64_t q = (((uint64_t)hi << 32) | lo) >> fshift;
+      const uint64_t d = q - fbase;
+      bin = d < (uint64_t)kFirstBins ? (uint32_t)d : 0xffffffffu;
+      above = q > fbase;
     }
-    const int id0 = __shfl_sync(0xffffffffu, id, 0);
-    if (__all_sync(0xffffffffu, id == id0)) {
-      if (id0 >= 0 && lane0) red_shared_add(a_hist + (uint32_t)id0 * 4u, 32u);
-    } else if (id >= 0) {
-      red_shared_add(a_hist + (uint32_t)id * 4u, 1u);
+    const bool inside = ok && bin < (uint32_t)kFirstBins;
+    red_shared_add_if(inside, a_hist + bin * 4u, 1u);
+    const bool outside = ok && !inside;
+    if (__any_sync(0xffffffffu, outside)) {
+      // keys outside the sampled range (zero-padded failures — possibly most of the row —, whatever the
+      // sample missed): one atomic per class and warp
+      const bool below = outside && !above;
+      const unsigned n_above = __popc(__ballot_sync(0xffffffffu, outside && above));
+      const unsigned n_below = __popc(__ballot_sync(0xffffffffu, below));
+      const unsigned n_zero = __popc(__ballot_sync(0xffffffffu, below && hi == 0x80000000u && lo == 0u));
+      const unsigned n_neg = __popc(__ballot_sync(0xffffffffu, below && hi < 0x80000000u));
+      // ... and the extreme keys out there: a target of rank 0 / n - 1 (a requested minimum / maximum,
+      // which a sample practically never sees) is then known without restarting the row
+      const unsigned long long k = ((unsigned long long)hi << 32) | lo;
+      unsigned long long k_lo = below ? k : ~0ull, k_hi = (outside && above) ? k : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, k_lo, o), h2 = __shfl_xor_sync(0xffffffffu, k_hi, o);
+        k_lo = l2 < k_lo ? l2 : k_lo;
+        k_hi = h2 > k_hi ? h2 : k_hi;
+      }
+      if (lane0) {
+        if (n_above) red_shared_add(a_hist + (uint32_t)kAboveAt * 4u, n_above);
+        if (n_below) red_shared_add(a_hist + (uint32_t)kBelowAt * 4u, n_below);
+        if (n_zero) red_shared_add(a_hist + (uint32_t)kBelowZeroAt * 4u, n_zero);
+        if (n_neg) red_shared_add(a_hist + (uint32_t)kBelowNegAt * 4u, n_neg);
+        if (n_below) atomicMin(&s_out[0], k_lo);
+        if (n_above) atomicMax(&s_out[1], k_hi);
+      }
     }
   });
 }
@@ -376,6 +409,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
                                                            int stride) {
   extern __shared__ uint32_t sh[];  // [n_groups][256]
   __shared__ PrefixTable T;
+  __shared__ unsigned long long s_out[2];
   SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
   if (rb >= 64 || R.ready) return;
@@ -407,16 +441,22 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
   const int ng = R.n_groups;
   const int used = first_digit ? kFirstWords : ng * 256;
   for (int k = threadIdx.x; k < used; k += kHistThreads) sh[k] = 0;
+  if (threadIdx.x == 0) { s_out[0] = ~0ull; s_out[1] = 0ull; }
   if (!first_digit && rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
   if (first_digit) {
     const uint32_t a_hist = smem_addr(sh);
     const uint64_t fbase = R.fbase;
     if (fshift >= 32) {
-      if (m) first_digit_elements<kHistThreads, true, true>(a_hist, fbase, fshift, x, m, cnt);
-      else first_digit_elements<kHistThreads, false, true>(a_hist, fbase, fshift, x, m, cnt);
+      if (m) first_digit_elements<kHistThreads, true, true>(a_hist, fbase, fshift, x, m, cnt, s_out);
+      else first_digit_elements<kHistThreads, false, true>(a_hist, fbase, fshift, x, m, cnt, s_out);
     } else {
-      if (m) first_digit_elements<kHistThreads, true, false>(a_hist, fbase, fshift, x, m, cnt);
-      else first_digit_elements<kHistThreads, false, false>(a_hist, fbase, fshift, x, m, cnt);
+      if (m) first_digit_elements<kHistThreads, true, false>(a_hist, fbase, fshift, x, m, cnt, s_out);
+      else first_digit_elements<kHistThreads, false, false>(a_hist, fbase, fshift, x, m, cnt, s_out);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_out[0] != ~0ull) atomicMin((unsigned long long*)&R.omin, s_out[0]);
+      if (s_out[1] != 0ull) atomicMax((unsigned long long*)&R.omax, s_out[1]);
     }
   } else {
     const int w = 64 - rb < 8 ? 64 - rb : 8;
@@ -428,16 +468,31 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
     if (sh[k]) atomicAdd(&H[k], sh[k]);
 }
 
-// After the full passes: gather the elements that share a live prefix into the row's list.
-template <bool MASKED, int MODE>
-__device__ __forceinline__ void collect_elements(const Probe& P, const double* __restrict__ x,
-                                                 const uint8_t* __restrict__ m, int cnt, SelRow& R,
-                                                 double* __restrict__ out, unsigned long long* s_min,
+// After the full passes: gather the elements that share a live prefix into the row's list. With several
+// live prefixes (the usual case) a 8 K-bit filter over the last 13 resolved key bits decides, for a whole
+// warp at once, that none of its elements is a candidate — ~95 % of the warps; the exact membership test
+// and the list append only run for the others.
+constexpr int kFilterBits = 13;
+constexpr int kFilterWords = (1 << kFilterBits) / 32;
+
+template <bool MASKED, int MODE, bool HI32>
+__device__ __forceinline__ void collect_elements(const Probe& P, uint32_t a_filter, uint32_t fmask,
+                                                 const double* __restrict__ x, const uint8_t* __restrict__ m, int cnt,
+                                                 SelRow& R, double* __restrict__ out, unsigned long long* s_min,
                                                  unsigned long long* s_max, const int* s_big) {
   const int cap = R.cap;
   const unsigned lane = threadIdx.x & 31u;
+  const int psh32 = P.pshift - 32;
   scan_elements<kHistThreads, MASKED>(x, m, cnt, [&](bool ok, double v, uint32_t hi, uint32_t lo) {
-    const int g = ok ? group_of<MODE>(P, hi, lo) : -1;
+    bool maybe = ok;
+    if (MODE == kScanOne) maybe = ok && (((hi ^ P.p_hi) & P.m_hi) | ((lo ^ P.p_lo) & P.m_lo)) == 0u;
+    if (MODE == kScanTable) {
+      uint32_t idx = HI32 ? (hi >> psh32) : (uint32_t)((((uint64_t)hi << 32) | lo) >> P.pshift);
+      idx &= fmask;
+      maybe = ok && ((lds_u32(a_filter + ((idx >> 5) << 2)) >> (idx & 31u)) & 1u) != 0u;
+    }
+    if (!__any_sync(0xffffffffu, maybe)) return;
+    const int g = maybe ? (MODE == kScanTable ? group_of<kScanTable>(P, hi, lo) : 0) : -1;
     bool take = false;
     if (g >= 0) {
       // bucket extremes (shared-memory atomics only — no plain read races them —, merged once per
@@ -465,6 +520,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
   __shared__ int s_big[kMaxTargets];
+  __shared__ uint32_t s_filter[kFilterWords];
   SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
   if (rb >= 64 || R.collected) return;
@@ -475,23 +531,33 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
     s_min[threadIdx.x] = ~0ull; s_max[threadIdx.x] = 0ull;
     s_big[threadIdx.x] = threadIdx.x < ng ? R.gbig[threadIdx.x] : 0;
   }
+  const bool table = rb > 0 && ng > 1;
+  const uint32_t fmask = (1u << (rb < kFilterBits ? rb : kFilterBits)) - 1u;
+  if (table)
+    for (int k = threadIdx.x; k < kFilterWords; k += kHistThreads) s_filter[k] = 0;
   if (rb > 0) build_table(T, R, ng, rb); else __syncthreads();
+  if (table && threadIdx.x < ng) {
+    const uint32_t idx = (uint32_t)R.uprefix[threadIdx.x] & fmask;
+    atomicOr(&s_filter[idx >> 5], 1u << (idx & 31u));
+  }
+  __syncthreads();
   const int64_t begin = (int64_t)blockIdx.x * chunk;
   const int cnt = (int)(begin + chunk < n ? chunk : n - begin);
   const double* __restrict__ x = R.d.x + begin;
   const uint8_t* __restrict__ m = R.d.mask ? R.d.mask + begin : nullptr;
   double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
   const Probe P = make_probe(R, rb, 0, T, nullptr);
-  if (rb == 0) {
-    if (m) collect_elements<true, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big);
-    else collect_elements<false, kScanTop>(P, x, m, cnt, R, out, s_min, s_max, s_big);
-  } else if (ng == 1) {
-    if (m) collect_elements<true, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big);
-    else collect_elements<false, kScanOne>(P, x, m, cnt, R, out, s_min, s_max, s_big);
-  } else {
-    if (m) collect_elements<true, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big);
-    else collect_elements<false, kScanTable>(P, x, m, cnt, R, out, s_min, s_max, s_big);
-  }
+  const uint32_t a_filter = smem_addr(s_filter);
+#define MCR_COLLECT(MODE, HI32)                                                                            \
+  do {                                                                                                     \
+    if (m) collect_elements<true, MODE, HI32>(P, a_filter, fmask, x, m, cnt, R, out, s_min, s_max, s_big);  \
+    else collect_elements<false, MODE, HI32>(P, a_filter, fmask, x, m, cnt, R, out, s_min, s_max, s_big);   \
+  } while (0)
+  if (rb == 0) MCR_COLLECT(kScanTop, false);
+  else if (ng == 1) MCR_COLLECT(kScanOne, false);
+  else if (P.pshift >= 32) MCR_COLLECT(kScanTable, true);
+  else MCR_COLLECT(kScanTable, false);
+#undef MCR_COLLECT
   __syncthreads();
   if (threadIdx.x < ng && s_min[threadIdx.x] != ~0ull) {
     atomicMin((unsigned long long*)&R.gmin[threadIdx.x], s_min[threadIdx.x]);
@@ -540,9 +606,11 @@ __device__ void set_target_ranks(SelRow& R, int64_t nv) {
   for (int q = 0; q < nq; ++q) {
     int64_t lo = 0, hi = 0;
     if (nv > 0) {
-      if (spec.median) {  // np.median: mean of the two middle order statistics
+      if (spec.median == 1) {  // np.median: mean of the two middle order statistics
         lo = (nv - 1) / 2;
         hi = nv / 2;
+      } else if (spec.median == 2) {  // {min, max}: the order statistics themselves
+        lo = hi = q == 0 ? 0 : nv - 1;
       } else {  // numpy 'linear': virtual index (n - 1) * q ; previous = floor(vi)
         const double vi = __dmul_rn((double)(nv - 1), spec.q[q]);
         if (vi >= (double)(nv - 1)) { lo = hi = nv - 1; }
@@ -580,6 +648,7 @@ __device__ void set_target_ranks(SelRow& R, int64_t nv) {
 //   other rows:     pass 0 histogrammed the top digit -> valid count, target ranks, first walk.
 __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   __shared__ int s_restart;
+  __shared__ uint32_t s_blocksum[kFirstBlocks];
   const QuantileSpec& spec = R.d.spec;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -594,9 +663,24 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   __syncthreads();
   if (rb < 64 && !R.ready) {
     if (counts_now) {
+      if (first_digit) {  // sums of the 256-bin blocks of the window histogram, all warps
+        for (int blk = warp; blk < kFirstBlocks; blk += (int)(blockDim.x >> 5)) {
+          uint32_t local = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int b = blk * 256 + lane * 8 + k;
+            local += b < kFirstBins ? H[b] : 0u;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+          if (lane == 0) s_blocksum[blk] = local;
+        }
+        __syncthreads();
+      }
       if (warp == 0) {
         int64_t part = 0;
-        for (int d = lane; d < (first_digit ? kFirstBins : 256); d += 32) part += H[d];
+        if (first_digit) part = lane < kFirstBlocks ? (int64_t)s_blocksum[lane] : 0;
+        else for (int d = lane; d < 256; d += 32) part += H[d];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
@@ -610,13 +694,20 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
             // ranks inside the prefix bucket. A target below it is +0.0 when its rank falls among the
             // zeros of the `below` mass (zero-padded failures: negative keys first, then the zeros,
             // then small positives); any other target outside the bucket restarts the row.
+            // ... except the row's own minimum / maximum when the whole row is on this GPU: the first
+            // digit pass tracked the extreme keys outside the window
             uint32_t fixed = 0;
+            const int64_t nv = R.n_valid;
             for (int t = 0; t < nt; ++t) {
-              if (R.n_valid > 0) {
-                if (R.rank[t] < below) {
-                  if (R.rank[t] >= below_neg && R.rank[t] < below_neg + below_zero) fixed |= 1u << t; else s_restart = 1;
-                } else if (R.rank[t] >= below + part) {
-                  s_restart = 1;
+              if (nv > 0) {
+                const int64_t r = R.rank[t];
+                if (r < below) {
+                  if (r >= below_neg && r < below_neg + below_zero) { fixed |= 1u << t; R.fixed_key[t] = kZeroKey; }
+                  else if (R.whole && r == 0) { fixed |= 1u << t; R.fixed_key[t] = R.omin; }
+                  else s_restart = 1;
+                } else if (r >= below + part) {
+                  if (R.whole && r == nv - 1) { fixed |= 1u << t; R.fixed_key[t] = R.omax; }
+                  else s_restart = 1;
                 }
               }
               R.rank[t] -= below;
@@ -625,14 +716,16 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
               fixed = 0;
               for (int t = 0; t < nt; ++t) { R.rank[t] += below; R.prefix[t] = 0; R.group[t] = 0; R.bcount[t] = R.n_valid; }
             } else if (fixed) {
-              // targets are rank-sorted and every target below the bucket is fixed here (else the row
-              // restarted), so the fixed ones come first: they shadow the first live target from
-              // here on (same bucket walk, no group of their own); all fixed: row done
-              const int t0 = __popc(fixed);
-              if (t0 >= nt) {
+              // a fixed target shadows a live one from here on (same bucket walk, no group of its own):
+              // targets are rank-sorted, so the fixed ones sit at the two ends; all fixed: row done
+              int first_live = -1, last_live = -1;
+              for (int t = 0; t < nt; ++t)
+                if (!((fixed >> t) & 1u)) { if (first_live < 0) first_live = t; last_live = t; }
+              if (first_live < 0) {
                 s_restart = 2;   // nothing left to select
               } else {
-                for (int t = 0; t < t0; ++t) R.rank[t] = R.rank[t0];
+                for (int t = 0; t < nt; ++t)
+                  if ((fixed >> t) & 1u) R.rank[t] = R.rank[t < first_live ? first_live : last_live];
               }
             }
             R.fixed_mask = fixed;
@@ -652,7 +745,25 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
       const int64_t r = R.rank[warp];
       int64_t running = 0;
       bool found = false;
-      for (int blk = 0; blk < nb && !found; blk += 256) {
+      int blk0 = 0;
+      if (first_digit) {  // the block holding the rank, from the block sums
+        const int64_t mine_sum = lane < kFirstBlocks ? (int64_t)s_blocksum[lane] : 0;
+        int64_t incl = mine_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, r >= incl - mine_sum && r < incl);
+        if (who) {
+          const int src = __ffs(who) - 1;
+          blk0 = src * 256;
+          running = __shfl_sync(0xffffffffu, incl - mine_sum, src);
+        } else {
+          blk0 = nb;  // beyond the histogram: falls through to the "not found" rule
+        }
+      }
+      for (int blk = blk0; blk < nb && !found; blk += 256) {
         uint32_t c[8];
         uint32_t local = 0;
 #pragma unroll
@@ -760,8 +871,9 @@ __device__ __forceinline__ double finish_value(const SelRow& R, int k) {
   const int64_t nv = R.n_valid;
   if (nv <= 0) return CUDART_NAN;
   const int sa = R.slot[2 * k], sb = R.slot[2 * k + 1];
-  const double a = ((R.fixed_mask >> sa) & 1u) ? 0.0 : value_of(R.prefix[sa]);   // fixed: +0.0 (kZeroKey)
-  const double b = ((R.fixed_mask >> sb) & 1u) ? 0.0 : value_of(R.prefix[sb]);
+  const double a = value_of(((R.fixed_mask >> sa) & 1u) ? R.fixed_key[sa] : R.prefix[sa]);
+  const double b = value_of(((R.fixed_mask >> sb) & 1u) ? R.fixed_key[sb] : R.prefix[sb]);
+  if (spec.median == 2) return a;
   if (spec.median) return (nv & 1) ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
   const double q = spec.q[k];
   const double vi = __dmul_rn((double)(nv - 1), q);
@@ -1073,18 +1185,19 @@ cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st,
 }
 
 // elements per CTA of a full scan: 16 K for rows of up to 16 M elements, else the row cut into
-// kMaxChunksPerRow pieces (a multiple of the 4 * kHistThreads-element tile of scan_elements)
+// kMaxChunksPerRow pieces (a multiple of the tile of scan_elements)
 static int chunk_for(int64_t max_n) {
   if (max_n <= (int64_t)kChunk * kMaxChunksPerRow) return kChunk;
   const int64_t c = (max_n + kMaxChunksPerRow - 1) / kMaxChunksPerRow;
-  const int64_t tile = 4 * kHistThreads;
+  const int64_t tile = MCR_SCAN_UNROLL * kHistThreads;
   return (int)((c + tile - 1) / tile * tile);
 }
 
 cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st, int sampled) {
   if (rows <= 0 || max_n <= 0) return cudaSuccess;
   int chunk = chunk_for(max_n), stride = 1;
-  if (pass == 1 && chunk < kFirstChunk) chunk = kFirstChunk;   // the (wide) first digit pass of adaptive rows
+  // the wide first digit pass of adaptive rows, and the later passes most rows skip: few, long CTAs
+  if (pass >= 1 && chunk < kFirstChunk) chunk = kFirstChunk;
   unsigned grid = (unsigned)((max_n + chunk - 1) / chunk);
   if (pass == 0) {
     // adaptive calls only sample the rows for their extreme keys in pass 0: ~64 pieces of 16 K

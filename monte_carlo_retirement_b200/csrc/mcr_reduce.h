@@ -11,7 +11,7 @@ constexpr int kMaxQuantiles = 16;
 
 struct QuantileSpec {
   int32_t n_q;
-  int32_t median;  // 1: np.median rule (mean of the two middle order statistics), q ignored
+  int32_t median;  // 1: np.median rule (mean of the two middle order statistics), q ignored; 2: {min, max}
   double q[kMaxQuantiles];
 };
 

@@ -18,6 +18,7 @@ FLAG_SMALL_RETURNS = 0x2
 STREAM_SEARCH = 0
 STREAM_FINAL = 1
 SEL_MEDIAN = 0x1
+SEL_MINMAX = 0x2  # specs: median="minmax"
 HIST_NUMPY = 0
 HIST_FLOOR = 1
 E_INVAL = -1
@@ -326,7 +327,8 @@ class Context:
                   median: bool = False) -> None:
         qs = (_D * len(q))(*[float(v) for v in q])
         self._check(self.lib.mcr_quantiles(self.handle, _ptr(values), n, ld, rows, _ptr(mask), qs, len(q),
-                                           SEL_MEDIAN if median else 0, _ptr(out), _ptr(counts), _stream_handle()))
+                                           SEL_MINMAX if median == "minmax" else (SEL_MEDIAN if median else 0), _ptr(out),
+                                           _ptr(counts), _stream_handle()))
 
     @staticmethod
     def select_rows(specs):
@@ -352,7 +354,7 @@ class Context:
             sl["mask_dev"] = 0 if mask is None else int(mask.data_ptr())
             sl["n"] = n
             sl["n_q"] = len(q)
-            sl["flags"] = SEL_MEDIAN if median else 0
+            sl["flags"] = SEL_MINMAX if median == "minmax" else (SEL_MEDIAN if median else 0)
             sl["q"][:, :len(q)] = np.asarray(q, dtype=np.float64)
             at += rows
         return arr

@@ -110,7 +110,6 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         super().__init__(params_model, main_seed_override, **kw)
         self.coll = collectives or Collectives()
         self._agreed: Dict[Any, int] = {}
-        self._sign4 = None
         self._shared_blocks: List["_SharedSummaryBlock"] = []   # rank-0-visible summary blocks (host, pinned)
         if self.rng_mode != "philox":
             raise ValueError("sharding needs the counter-based Philox draws (rng='philox')")
@@ -156,21 +155,8 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         return self.coll.sum_(block)
 
     def _final_balance_histograms(self, b, rng_m, rng_1, hists) -> None:
-        import torch
-
+        # (the ranges are GLOBAL already: min / max of the cohort come out of the distributed select)
         ctx, coll, n = self.native_context, self.coll, b.n
-        ctx.minmax(b.cols[1], n, rng_m, mask=b.success, divisor=1e6)
-        ctx.minmax(b.cols[1], n, rng_1, mask=b.success, divisor=1.0)
-        # global ranges in ONE all-reduce(MIN) of [lo_m, -hi_m, lo_1, -hi_1]; NaN (empty local
-        # cohort) must not poison it
-        if self._sign4 is None:
-            self._sign4 = torch.tensor([1.0, -1.0, 1.0, -1.0], dtype=torch.float64, device=rng_m.device)
-        sign = self._sign4
-        packed = torch.nan_to_num(torch.cat([rng_m, rng_1]) * sign, nan=float("inf"))
-        coll.min_(packed)
-        packed = torch.where(torch.isinf(packed), float("nan"), packed * sign)
-        rng_m.copy_(packed[0:2])
-        rng_1.copy_(packed[2:4])
         ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
         ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
         coll.sum_(hists)

@@ -774,13 +774,16 @@ class RetirementMonteCarloSimulator:
         cnt = torch.empty(3, dtype=torch.int64, device=dev)
         # every order statistic of the step in ONE multi-row select: 3 medians (different columns /
         # cohorts), the 9 final-balance quantiles and, when the series are resident, the bands
+        # (row 4: min and max of the successful cohort's final balances — the ranges of the two histograms)
         specs = [(rates, n, None, [0.5], True), (b.cols[0], n, None, [0.5], True),
-                 (b.cols[1], n, b.success, [0.5], True), (b.cols[1], n, None, FINAL_BALANCE_QUANTILES, False)]
+                 (b.cols[1], n, b.success, [0.5], True), (b.cols[1], n, None, FINAL_BALANCE_QUANTILES, False),
+                 (b.cols[1], n, b.success, [0.0, 1.0], "minmax")]
+        B0 = len(specs)  # first band row
         with_bands = bool(bands) and len(plan) == 1
         if with_bands:
             specs += (ctx.series_rows(b.traj, n, T, TRAJECTORY_QUANTILES) + ctx.series_rows(b.real, n, T, TRAJECTORY_QUANTILES)
                       + ctx.series_rows(b.wr, n, R, WITHDRAWAL_RATE_QUANTILES))
-        desc = ctx.select_rows(specs)  # one descriptor per row (4 + 2T + R of them with the bands)
+        desc = ctx.select_rows(specs)  # one descriptor per row (5 + 2T + R of them with the bands)
         out16 = torch.empty((len(desc), 16), **f64)
         cnt_all = torch.empty(len(desc), dtype=torch.int64, device=dev)
         flag = self._select(desc, out16, cnt_all, stepwise=stepwise)
@@ -794,8 +797,16 @@ class RetirementMonteCarloSimulator:
         small[0:3].copy_(out16[0:3, 0])
         cnt.copy_(cnt_all[0:3])
         small[3:3 + nf].copy_(out16[3, :nf])
+        # histogram ranges: [min, max] in $M (plotting.py:46-59: final / 1e6 — a division by a positive
+        # constant is monotone, so min(x / 1e6) == min(x) / 1e6 bit for bit) and in $ (HistogramChart.jsx)
         rng_m = small[3 + nf:3 + nf + 2]
         rng_1 = small[3 + nf + 2:3 + nf + 4]
+        rng_1.copy_(out16[4, 0:2])
+        # (a DEVICE divisor: torch turns a division by a host scalar into a multiplication by its reciprocal,
+        # which is not the correctly rounded quotient the histogram kernel computes for every element)
+        if getattr(self, "_million", None) is None or self._million.device != dev:
+            self._million = torch.full((1,), 1e6, **f64)
+        torch.div(out16[4, 0:2], self._million, out=rng_m)
         hists = torch.zeros(160, dtype=torch.int64, device=dev)
         self._final_balance_histograms(b, rng_m, rng_1, hists)
         band_block = wr_counts = sample_block = None
@@ -808,10 +819,10 @@ class RetirementMonteCarloSimulator:
                 if sample_block is not None:
                     self._gather_samples(b.traj, n, T, offset, n_global, sample_block[0])
                     self._gather_samples(b.real, n, T, offset, n_global, sample_block[1])
-                band_block[:T * nq].view(T, nq).copy_(out16[4:4 + T, :nq])
-                band_block[T * nq:2 * T * nq].view(T, nq).copy_(out16[4 + T:4 + 2 * T, :nq])
-                band_block[2 * T * nq:].view(R, nw).copy_(out16[4 + 2 * T:, :nw])
-                wr_counts.copy_(cnt_all[4 + 2 * T:])
+                band_block[:T * nq].view(T, nq).copy_(out16[B0:B0 + T, :nq])
+                band_block[T * nq:2 * T * nq].view(T, nq).copy_(out16[B0 + T:B0 + 2 * T, :nq])
+                band_block[2 * T * nq:].view(R, nw).copy_(out16[B0 + 2 * T:, :nw])
+                wr_counts.copy_(cnt_all[B0 + 2 * T:])
             else:
                 # the three series do not fit together: one multi-row select per pass of the plan;
                 # the first pass's series came with the summary batch, the others are recomputed
@@ -863,9 +874,7 @@ class RetirementMonteCarloSimulator:
         histogram (HistogramChart.jsx:13-60) of the successful cohort's final balances."""
         ctx = self.native_context
         n = b.n
-        ctx.minmax(b.cols[1], n, rng_m, mask=b.success, divisor=1e6)
         ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
-        ctx.minmax(b.cols[1], n, rng_1, mask=b.success, divisor=1.0)
         ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
 
     def run_aggregates(self, working_months: int, num_simulations: int, *, bands: bool = True,

@@ -319,6 +319,13 @@ def test_quantiles_whatever_the_first_digit_window_looks_like(n):
     sim.native_context.quantiles(_dev(x), n, n, len(rows), [0.5], med, mask=_dev(mask, np.uint8), median=True)
     want_med = np.array([np.median(r[mask]) for r in x])
     assert np.array_equal(med.cpu().numpy()[:, 0], want_med)
+    # MCR_SEL_MINMAX rows (the histogram ranges of a step): the exact extreme elements of the cohort
+    ctx = sim.native_context
+    xd, md = _dev(x), _dev(mask, np.uint8)
+    mm = torch.empty((len(rows), 16), dtype=torch.float64, device="cuda")
+    ctx.quantiles_rows(ctx.select_rows([(xd, n, md, [0.0, 1.0], "minmax")]), mm)
+    got_mm = mm.cpu().numpy()[:, :2]
+    assert np.array_equal(got_mm[:, 0], x[:, mask].min(axis=1)) and np.array_equal(got_mm[:, 1], x[:, mask].max(axis=1))
 
 
 def test_histograms_match_numpy_and_frontend_rule():

@@ -20,7 +20,7 @@ LIB = os.path.join(LIB_DIR, "libmcr_b200.so")
 
 def build(env_extra):
     env = dict(os.environ)
-    for k in ("MCR_MIN_BLOCKS", "MCR_BLOCK"):
+    for k in ("MCR_MIN_BLOCKS", "MCR_BLOCK", "MCR_SCAN_UNROLL", "MCR_FIRST_CHUNK"):
         env.pop(k, None)
     env.update(env_extra)
     subprocess.run([sys.executable, "-m", "monte_carlo_retirement_b200.build", "--force"], cwd=ROOT, env=env, check=True,

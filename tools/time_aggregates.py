@@ -32,3 +32,9 @@ print(f"  real bands  {t(lambda: ctx.quantiles(b.real, n, n, T, TRAJECTORY_QUANT
 print(f"  wr bands    {t(lambda: ctx.quantiles(b.wr, n, n, R, WITHDRAWAL_RATE_QUANTILES, outw)):.3f} ms  ({R} rows)")
 m = torch.empty(1, dtype=torch.float64, device="cuda")
 print(f"  1-row median {t(lambda: ctx.quantiles(b.cols[1], n, n, 1, [0.5], m, median=True)):.3f} ms")
+agg = sim.aggregates_device(a.wm, n, bands=True)
+plan = sim.last_series_plan
+kw = dict(n_global=n, offset=0, working_months=a.wm, bands=True, plan=plan, samples=False, part_first=0)
+l0 = ctx.launch_count
+ms = t(lambda: sim._aggregate_batch(agg.batch, **kw), reps=10)
+print(f"  ALL aggregations of a step on the resident batch: {ms:.3f} ms, {(ctx.launch_count - l0) // 11} library launches")
