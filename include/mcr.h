@@ -329,7 +329,7 @@ int mcr_quantiles_rows(mcr_ctx* ctx, const mcr_select_row* rows_host, int32_t n_
 int64_t mcr_select_exchange_words(int32_t rows, int32_t world);
 void mcr_select_exchange_layout(int32_t rows, int32_t world, int64_t* at4);
 int32_t mcr_select_full_passes(void);
-/* the same for rows of up to n_global_max elements over all ranks: rows above 2^27 elements get
+/* the same for rows of up to n_global_max elements over all ranks: rows above 2^24 elements get
  * one more digit pass before the collect, so that their buckets still fit the candidate lists */
 int32_t mcr_select_full_passes_for(int64_t n_global_max);
 /* HIST of pass 0 of a call begun adaptively: OR this into `pass` so that only the CTAs of the

@@ -103,9 +103,10 @@ constexpr int kMaxChunksPerRow = 1024;  // a long row is cut into at most this m
 constexpr int kCandCap = 16384;     // candidate list capacity per row (doubles)
 constexpr int kPoolCap = 8192;      // ... of the list the ranks of a multi-GPU call pool (all-reduced: kept small)
 constexpr int kBigBucket = 4096;    // buckets above this are not gathered (resolved by min == max, else by scanning)
-constexpr int kFullPasses = 4;      // passes that may scan the rows before the collect (pass 0 + up to 3 digits);
-constexpr int kFullPassesLong = 5;  // one more digit for rows of more than 2^27 elements (GLOBAL length)
-constexpr int64_t kLongRow = (int64_t)1 << 27;
+constexpr int kFullPasses = 3;      // passes that may scan the rows before the collect: the sample, the ~13-bit first digit
+                                    // pass and one 8-bit digit (21 bits over the sampled range);
+constexpr int kFullPassesLong = 4;  // one more digit for rows of more than 2^24 elements (GLOBAL length), so that their
+constexpr int64_t kLongRow = (int64_t)1 << 24;   // buckets still fit the candidate lists
 constexpr int kHistWords = kMaxTargets * 256;  // per row
 constexpr int kSampleStride = 16;   // adaptive pass 0 reads every 16th chunk of a long row ...
 constexpr int kSampleMinChunks = 8; // ... rows of up to 8 chunks are read whole
@@ -160,6 +161,12 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
 }
 __device__ __forceinline__ void lds_u64(uint32_t a, uint32_t& lo, uint32_t& hi) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a) : "memory");
+}
+// a value the compiler must keep in a register (a shared-window address it would otherwise rebuild from
+// SR_CgaCtaId + constants — 4 instructions — at every use inside an unrolled loop)
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
   if (threadIdx.x == 0) { s_out[0] = ~0ull; s_out[1] = 0ull; }
   if (!first_digit && rb > 0 && ng > 1) build_table(T, R, ng, rb); else __syncthreads();
   if (first_digit) {
-    const uint32_t a_hist = smem_addr(sh);
+    const uint32_t a_hist = opaque(smem_addr(sh));
     const uint64_t fbase = R.fbase;
     if (fshift >= 32) {
       if (m) first_digit_elements<kHistThreads, true, true>(a_hist, fbase, fshift, x, m, cnt, s_out);
@@ -469,10 +476,10 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
 }
 
 // After the full passes: gather the elements that share a live prefix into the row's list. With several
-// live prefixes (the usual case) a 8 K-bit filter over the last 13 resolved key bits decides, for a whole
+// live prefixes (the usual case) a 64 K-bit filter over the last 16 resolved key bits decides, for a whole
 // warp at once, that none of its elements is a candidate — ~95 % of the warps; the exact membership test
 // and the list append only run for the others.
-constexpr int kFilterBits = 13;
+constexpr int kFilterBits = 16;
 constexpr int kFilterWords = (1 << kFilterBits) / 32;
 
 template <bool MASKED, int MODE, bool HI32>
@@ -489,7 +496,8 @@ __device__ __forceinline__ void collect_elements(const Probe& P, uint32_t a_filt
     if (MODE == kScanTable) {
       uint32_t idx = HI32 ? (hi >> psh32) : (uint32_t)((((uint64_t)hi << 32) | lo) >> P.pshift);
       idx &= fmask;
-      maybe = ok && ((lds_u32(a_filter + ((idx >> 5) << 2)) >> (idx & 31u)) & 1u) != 0u;
+      const uint32_t bit = (lds_u32(a_filter + ((idx >> 5) << 2)) >> (idx & 31u)) & 1u;   // (NaN lanes too: no branch)
+      maybe = ok & (bit != 0u);
     }
     if (!__any_sync(0xffffffffu, maybe)) return;
     const int g = maybe ? (MODE == kScanTable ? group_of<kScanTable>(P, hi, lo) : 0) : -1;
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict
   const uint8_t* __restrict__ m = R.d.mask ? R.d.mask + begin : nullptr;
   double* __restrict__ out = cand + (size_t)blockIdx.y * kCandCap;
   const Probe P = make_probe(R, rb, 0, T, nullptr);
-  const uint32_t a_filter = smem_addr(s_filter);
+  const uint32_t a_filter = opaque(smem_addr(s_filter));
 #define MCR_COLLECT(MODE, HI32)                                                                            \
   do {                                                                                                     \
     if (m) collect_elements<true, MODE, HI32>(P, a_filter, fmask, x, m, cnt, R, out, s_min, s_max, s_big);  \
@@ -860,9 +868,23 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   __syncthreads();
 }
 
+// (the per-row state is a few KB that one thread walks back and forth: staged in shared memory)
+__device__ __forceinline__ void stage_row(SelRow& dst, const SelRow& src) {
+  static_assert(sizeof(SelRow) % 8 == 0, "SelRow is copied in 8-byte words");
+  const uint64_t* s = (const uint64_t*)&src;
+  uint64_t* d = (uint64_t*)&dst;
+  for (int k = threadIdx.x; k < (int)(sizeof(SelRow) / 8); k += blockDim.x) d[k] = s[k];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) k_sel_advance(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
                                                       int pass) {
-  advance_row(rows[blockIdx.x], hist + (size_t)blockIdx.x * kHistWords, pass);
+  __shared__ SelRow s_row;
+  // finished rows and rows waiting for the collect: no CTA touched their histogram (still all zero)
+  if (rows[blockIdx.x].rb >= 64 || rows[blockIdx.x].ready) return;
+  stage_row(s_row, rows[blockIdx.x]);
+  advance_row(s_row, hist + (size_t)blockIdx.x * kHistWords, pass);
+  stage_row(rows[blockIdx.x], s_row);
 }
 
 // numpy 'linear' interpolation / np.median rule for quantile `k` of a finished row
@@ -902,7 +924,9 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
   __shared__ int need_scan;
   __shared__ int s_one[kMaxTargets];         // target sits in an ungathered bucket of one repeated value ...
   __shared__ uint64_t s_one_key[kMaxTargets];  // ... this one
-  SelRow& R = rows[blockIdx.x];
+  __shared__ SelRow s_row;
+  stage_row(s_row, rows[blockIdx.x]);
+  SelRow& R = s_row;   // (nothing reads the row state after the tail: no copy back)
   const QuantileSpec& spec = R.d.spec;
   const int tid = threadIdx.x;
   const int nt = 2 * spec.n_q;
