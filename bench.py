@@ -92,6 +92,9 @@ class ClockSampler:
         self.bits = 0
         self.stop_flag = threading.Event()
         self.thread = None
+        # NVML queries take driver locks the launching thread also needs: poll sparsely (the timed region of the
+        # default run is > 100 ms, so it still gets several samples)
+        self.period_s = float(os.environ.get("MCR_BENCH_SAMPLE_MS", "25")) / 1e3
 
     def _nvml_handle(self):
         import pynvml
@@ -132,7 +135,7 @@ class ClockSampler:
                 self.bits |= int(reasons(self.handle))
             except Exception:
                 pass
-            self.stop_flag.wait(0.01)
+            self.stop_flag.wait(self.period_s)
 
     def _pump(self):
         for line in self.proc.stdout:

@@ -85,6 +85,8 @@ struct SelRow {
   int32_t fshift;                   //   (64: no window — nothing sampled, or the row restarted from bit 0)
   int32_t cap;                      // candidate list capacity of this call (kCandCap; kPoolCap when ranks pool lists)
   int32_t whole;                    // the row is complete on this GPU (single-GPU call): omin / omax are the row's
+  uint32_t done;                    // CTAs of the current scan that have finished this row (fused launches, see k_sel_hist)
+  uint32_t pad1;
   int64_t n_valid;
   int32_t n_groups;
   int32_t rb;                       // resolved bits (64 == done)
@@ -142,7 +144,7 @@ __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ his
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
     R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused != 0; R.ready = 0; R.fixed_mask = 0;
     R.fbase = 0; R.fshift = 64; R.cap = (fused & 2) ? kPoolCap : kCandCap;
-    R.omin = ~0ull; R.omax = 0ull; R.whole = fused == 1;
+    R.omin = ~0ull; R.omax = 0ull; R.whole = fused == 1; R.done = 0;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
@@ -411,15 +413,11 @@ __device__ __forceinline__ void first_digit_elements(uint32_t a_hist, uint64_t f
 // (one CTA).
 // chunk: elements per CTA (a multiple of 4 * kHistThreads); stride: pass 0 of an adaptive call
 // launches one CTA per `stride` chunks (the sample), every other pass has stride 1.
-__global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
-                                                           const double* __restrict__ cand, int pass, int chunk,
-                                                           int stride) {
-  extern __shared__ uint32_t sh[];  // [n_groups][256]
+__device__ __forceinline__ void hist_cta(SelRow& R, uint32_t* __restrict__ H, const double* __restrict__ cand, int pass,
+                                         int chunk, int stride, uint32_t* sh) {
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_out[2];
-  SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
-  if (rb >= 64 || R.ready) return;
   const bool from_cand = R.collected && !R.overflow;
   if (from_cand && blockIdx.x > 0) return;
   const int64_t n = R.d.n;
@@ -435,7 +433,6 @@ __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ 
   }
   if (from_cand) begin = 0;
   if (!from_cand && begin >= n) return;
-  uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
   const int cnt = from_cand ? R.n_cand : (int)(begin + chunk < n ? chunk : n - begin);
   const double* __restrict__ x = (from_cand ? cand + (size_t)blockIdx.y * kCandCap : R.d.x) + begin;
   const uint8_t* __restrict__ m = (from_cand || !R.d.mask) ? nullptr : R.d.mask + begin;
@@ -523,15 +520,12 @@ __device__ __forceinline__ void collect_elements(const Probe& P, uint32_t a_filt
   });
 }
 
-__global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand,
-                                                              int chunk) {
+__device__ __forceinline__ void collect_cta(SelRow& R, double* __restrict__ cand, int chunk) {
   __shared__ PrefixTable T;
   __shared__ unsigned long long s_min[kMaxTargets], s_max[kMaxTargets];
   __shared__ int s_big[kMaxTargets];
   __shared__ uint32_t s_filter[kFilterWords];
-  SelRow& R = rows[blockIdx.y];
   const int rb = R.rb;
-  if (rb >= 64 || R.collected) return;
   const int64_t n = R.d.n;
   if ((int64_t)blockIdx.x * chunk >= n) return;
   const int ng = R.n_groups;
@@ -590,18 +584,22 @@ __global__ void k_sel_extremes(SelRow* __restrict__ rows, long long* __restrict_
   }
 }
 
+// one thread, after every CTA of the collect has finished the row
+__device__ __forceinline__ void collect_finish_row(SelRow& R) {
+  const int n_cand = atomicAdd(&R.n_cand, 0);   // (the cursor the scan CTAs advanced: read at L2)
+  if (n_cand > R.cap) { R.n_cand = R.cap; R.overflow = 1; }
+  // stepwise (multi-GPU) protocol: later passes histogram the list, so a row with a bucket
+  // that was not gathered keeps scanning the full row instead
+  if (!R.fused)
+    for (int g = 0; g < R.n_groups; ++g)
+      if (R.gbig[g]) R.overflow = 1;
+  R.collected = 1;
+  R.ready = 0;  // later (stepwise) passes histogram the candidate list
+}
+
 __global__ void k_sel_collect_finish(SelRow* __restrict__ rows) {
   SelRow& R = rows[blockIdx.x];
-  if (threadIdx.x == 0 && R.rb < 64 && !R.collected) {
-    if (R.n_cand > R.cap) { R.n_cand = R.cap; R.overflow = 1; }
-    // stepwise (multi-GPU) protocol: later passes histogram the list, so a row with a bucket
-    // that was not gathered keeps scanning the full row instead
-    if (!R.fused)
-      for (int g = 0; g < R.n_groups; ++g)
-        if (R.gbig[g]) R.overflow = 1;
-    R.collected = 1;
-    R.ready = 0;  // later (stepwise) passes histogram the candidate list
-  }
+  if (threadIdx.x == 0 && R.rb < 64 && !R.collected) collect_finish_row(R);
 }
 
 // the 0-based order statistics a row asks for, given its valid count: (lo, hi) per quantile,
@@ -654,6 +652,14 @@ __device__ void set_target_ranks(SelRow& R, int64_t nv) {
 //                   target that falls outside the window (only possible if the sample missed that
 //                   much of the row) restarts the row from bit 0 as a non-adaptive one;
 //   other rows:     pass 0 histogrammed the top digit -> valid count, target ranks, first walk.
+// HG: H is the row's histogram in GLOBAL memory, merged by the atomics of other CTAs — of the SAME launch when
+// the advance is fused into the scan kernel: read through L2.
+template <bool HG>
+__device__ __forceinline__ uint32_t ld_hist(const uint32_t* p) {
+  return HG ? __ldcg(p) : *p;
+}
+
+template <bool HG>
 __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
   __shared__ int s_restart;
   __shared__ uint32_t s_blocksum[kFirstBlocks];
@@ -677,7 +683,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int b = blk * 256 + lane * 8 + k;
-            local += b < kFirstBins ? H[b] : 0u;
+            local += b < kFirstBins ? ld_hist<HG>(H + b) : 0u;
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
@@ -688,13 +694,13 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
       if (warp == 0) {
         int64_t part = 0;
         if (first_digit) part = lane < kFirstBlocks ? (int64_t)s_blocksum[lane] : 0;
-        else for (int d = lane; d < 256; d += 32) part += H[d];
+        else for (int d = lane; d < 256; d += 32) part += ld_hist<HG>(H + d);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
-          const int64_t below = first_digit ? (int64_t)H[kBelowAt] : 0, above = first_digit ? (int64_t)H[kAboveAt] : 0;
-          const int64_t below_neg = first_digit ? (int64_t)H[kBelowNegAt] : 0;
-          const int64_t below_zero = first_digit ? (int64_t)H[kBelowZeroAt] : 0;
+          const int64_t below = first_digit ? (int64_t)ld_hist<HG>(H + kBelowAt) : 0, above = first_digit ? (int64_t)ld_hist<HG>(H + kAboveAt) : 0;
+          const int64_t below_neg = first_digit ? (int64_t)ld_hist<HG>(H + kBelowNegAt) : 0;
+          const int64_t below_zero = first_digit ? (int64_t)ld_hist<HG>(H + kBelowZeroAt) : 0;
           set_target_ranks(R, part + below + above);
           if (!adaptive) {
             for (int t = 0; t < nt; ++t) { R.prefix[t] = 0; R.group[t] = 0; }
@@ -747,7 +753,9 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
     // warp t walks target t's bucket histogram (8 bins per lane + warp scan, 256 bins at a time) to
     // the bin holding its rank
     const int w = 64 - rb < 8 ? 64 - rb : 8;
-    if (!extremes_only && !restart && !all_fixed && warp < nt && R.n_valid > 0) {
+    const int n_warps = (int)(blockDim.x >> 5);
+    for (int tw = warp; tw < nt && !extremes_only && !restart && !all_fixed && R.n_valid > 0; tw += n_warps) {
+      const int warp = tw;   // (the target this warp walks in this round)
       const uint32_t* h = first_digit ? H : H + R.group[warp] * 256;
       const int nb = first_digit ? kFirstBins : 256;
       const int64_t r = R.rank[warp];
@@ -777,7 +785,7 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int b = blk + lane * 8 + k;
-          c[k] = b < nb ? h[b] : 0u;
+          c[k] = b < nb ? ld_hist<HG>(h + b) : 0u;
           local += c[k];
         }
         uint32_t incl = local;
@@ -869,11 +877,13 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
 }
 
 // (the per-row state is a few KB that one thread walks back and forth: staged in shared memory)
+// CG: read the source through L2 (it was updated by atomics of other CTAs of the same launch)
+template <bool CG>
 __device__ __forceinline__ void stage_row(SelRow& dst, const SelRow& src) {
   static_assert(sizeof(SelRow) % 8 == 0, "SelRow is copied in 8-byte words");
-  const uint64_t* s = (const uint64_t*)&src;
-  uint64_t* d = (uint64_t*)&dst;
-  for (int k = threadIdx.x; k < (int)(sizeof(SelRow) / 8); k += blockDim.x) d[k] = s[k];
+  const unsigned long long* s = (const unsigned long long*)&src;
+  unsigned long long* d = (unsigned long long*)&dst;
+  for (int k = threadIdx.x; k < (int)(sizeof(SelRow) / 8); k += blockDim.x) d[k] = CG ? __ldcg(s + k) : s[k];
   __syncthreads();
 }
 
@@ -882,9 +892,55 @@ __global__ void __launch_bounds__(1024) k_sel_advance(SelRow* __restrict__ rows,
   __shared__ SelRow s_row;
   // finished rows and rows waiting for the collect: no CTA touched their histogram (still all zero)
   if (rows[blockIdx.x].rb >= 64 || rows[blockIdx.x].ready) return;
-  stage_row(s_row, rows[blockIdx.x]);
-  advance_row(s_row, hist + (size_t)blockIdx.x * kHistWords, pass);
-  stage_row(rows[blockIdx.x], s_row);
+  stage_row<false>(s_row, rows[blockIdx.x]);
+  advance_row<true>(s_row, hist + (size_t)blockIdx.x * kHistWords, pass);
+  stage_row<false>(rows[blockIdx.x], s_row);
+}
+
+// "this CTA is the last one of its row's grid line to finish": every CTA of the line calls it once, after its
+// global atomics; true for exactly one of them, which then sees everything the others published
+__device__ __forceinline__ bool last_cta_of_row(SelRow& R) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&R.done, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  const bool last = s_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// One pass, first half (hist_cta) — and, in the single-GPU launch sequence (`fuse`), the second half too: the
+// last CTA to finish a row walks the row's merged histogram right away (advance_row), while the other rows
+// are still being scanned; no separate advance launch, and its serial part stays off the critical path.
+__global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
+                                                           const double* __restrict__ cand, int pass, int chunk,
+                                                           int stride, int fuse) {
+  extern __shared__ uint32_t sh[];  // [n_groups][256] or the kFirstWords of the first digit pass
+  __shared__ SelRow s_row;
+  SelRow& R = rows[blockIdx.y];
+  if (R.rb >= 64 || R.ready) return;   // the whole grid line of the row returns here: nothing to advance
+  uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
+  hist_cta(R, H, cand, pass, chunk, stride, sh);
+  if (!fuse || !last_cta_of_row(R)) return;
+  stage_row<true>(s_row, R);
+  advance_row<true>(s_row, H, pass);
+  if (threadIdx.x == 0) s_row.done = 0;
+  __syncthreads();
+  stage_row<false>(R, s_row);
+}
+
+// The gather scan (collect_cta); `fuse`: the last CTA of a row also closes its list (k_sel_collect_finish).
+__global__ void __launch_bounds__(kHistThreads) k_sel_collect(SelRow* __restrict__ rows, double* __restrict__ cand,
+                                                              int chunk, int fuse) {
+  SelRow& R = rows[blockIdx.y];
+  if (R.rb >= 64 || R.collected) return;   // the whole grid line of the row
+  collect_cta(R, cand, chunk);
+  if (!fuse || !last_cta_of_row(R)) return;
+  if (threadIdx.x == 0) {
+    collect_finish_row(R);
+    R.done = 0;
+  }
 }
 
 // numpy 'linear' interpolation / np.median rule for quantile `k` of a finished row
@@ -925,7 +981,7 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
   __shared__ int s_one[kMaxTargets];         // target sits in an ungathered bucket of one repeated value ...
   __shared__ uint64_t s_one_key[kMaxTargets];  // ... this one
   __shared__ SelRow s_row;
-  stage_row(s_row, rows[blockIdx.x]);
+  stage_row<false>(s_row, rows[blockIdx.x]);
   SelRow& R = s_row;   // (nothing reads the row state after the tail: no copy back)
   const QuantileSpec& spec = R.d.spec;
   const int tid = threadIdx.x;
@@ -963,7 +1019,7 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
           hist_dispatch<kTailThreads>(P, x + b0, mask ? mask + b0 : nullptr, cnt, cur, ng);
         }
         __syncthreads();
-        advance_row(R, s_hist, pass);
+        advance_row<false>(R, s_hist, pass);
       }
       // (a one-value bucket is not in the list: its targets walked empty histograms above)
       if (from_list && tid < nt && s_one[tid]) R.prefix[tid] = s_one_key[tid];
@@ -1217,7 +1273,8 @@ static int chunk_for(int64_t max_n) {
   return (int)((c + tile - 1) / tile * tile);
 }
 
-cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st, int sampled) {
+cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st, int sampled,
+                            int fuse) {
   if (rows <= 0 || max_n <= 0) return cudaSuccess;
   int chunk = chunk_for(max_n), stride = 1;
   // the wide first digit pass of adaptive rows, and the later passes most rows skip: few, long CTAs
@@ -1245,17 +1302,18 @@ cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void
   }
   const size_t smem = (size_t)kHistWords * sizeof(uint32_t);
   k_sel_hist<<<dim3(grid, (unsigned)rows), kHistThreads, smem, st>>>((SelRow*)state, (uint32_t*)hist,
-                                                                     cand_of(state, rows), pass, chunk, stride);
+                                                                     cand_of(state, rows), pass, chunk, stride, fuse);
   return cudaGetLastError();
 }
 
-cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st) {
+cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st, int fuse) {
   if (rows <= 0) return cudaSuccess;
   const int chunk = chunk_for(max_n);
   const unsigned chunks = (unsigned)((max_n + chunk - 1) / chunk);
   if (chunks > 0)
-    k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>((SelRow*)state, cand_of(state, rows), chunk);
-  k_sel_collect_finish<<<rows, 32, 0, st>>>((SelRow*)state);
+    k_sel_collect<<<dim3(chunks, (unsigned)rows), kHistThreads, 0, st>>>((SelRow*)state, cand_of(state, rows), chunk,
+                                                                         fuse);
+  if (!fuse || chunks == 0) k_sel_collect_finish<<<rows, 32, 0, st>>>((SelRow*)state);
   return cudaGetLastError();
 }
 
@@ -1286,15 +1344,20 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
   }
   cudaError_t e = launch_sel_begin(rows, state, hist, st, /*adaptive=*/1, /*fused=*/1);
   ++*n_launches;
+  // hist passes with the advance, and the collect with its finish, fused into the scan kernels (their last
+  // CTA per row): init + (sample, first digit, [digit ...]) + collect + tail launches in all
   const int full = select_full_passes_for(max_n);
   for (int pass = 0; pass < full && e == cudaSuccess; ++pass) {
-    e = launch_sel_hist(rows, max_n, pass, state, hist, st, /*sampled=*/1);
-    *n_launches += max_n > 0;
-    if (e == cudaSuccess) e = launch_sel_advance(rows, max_nq, pass, state, hist, st);
-    ++*n_launches;
+    if (max_n > 0) {
+      e = launch_sel_hist(rows, max_n, pass, state, hist, st, /*sampled=*/1, /*fuse=*/1);
+      ++*n_launches;
+    } else {
+      e = launch_sel_advance(rows, max_nq, pass, state, hist, st);   // empty rows: nothing to scan
+      ++*n_launches;
+    }
   }
-  if (e == cudaSuccess) e = launch_sel_collect(rows, max_n, state, st);
-  *n_launches += 1 + (max_n > 0);
+  if (e == cudaSuccess) e = launch_sel_collect(rows, max_n, state, st, /*fuse=*/1);
+  ++*n_launches;
   if (e != cudaSuccess) return e;
   // one launch for the remaining digits + interpolation (see k_sel_tail)
   k_sel_tail<<<rows, kTailThreads, sizeof(uint32_t) * kHistWords, st>>>((SelRow*)state, cand_of(state, rows), kCandCap, out,

@@ -32,9 +32,11 @@ cudaError_t launch_quantiles_rows(int rows, const RowDesc* desc_host, double* ou
                                   void* state, void* hist, cudaStream_t st, int* n_launches);
 // the same select, one pass at a time (a multi-GPU caller all-reduces `hist` between hist and advance)
 cudaError_t launch_sel_begin(int rows, void* state, void* hist, cudaStream_t st, int adaptive = 0, int fused = 0);
+// fuse: the last CTA of a row runs the advance / closes the list itself (single-GPU sequence: no separate
+// ADVANCE launch, no all-reduce in between)
 cudaError_t launch_sel_hist(int rows, int64_t max_n, int pass, void* state, void* hist, cudaStream_t st,
-                            int sampled = 0);
-cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st);
+                            int sampled = 0, int fuse = 0);
+cudaError_t launch_sel_collect(int rows, int64_t max_n, void* state, cudaStream_t st, int fuse = 0);
 int select_full_passes();
 int select_full_passes_for(int64_t n_global_max);
 // pooled tail for path shards on several GPUs (see "candidate exchange" in mcr_reduce.cu)

@@ -536,6 +536,12 @@ class RetirementMonteCarloSimulator:
 
         if not bands:
             return [()]
+        # decided once per call shape: cudaMemGetInfo takes 10-60 ms while kernels are running — on the host
+        # thread that is supposed to keep the launch queue full (aggregates_device re-plans after an OOM)
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        ckey = None if key is None else (key, os.environ.get("MCR_SERIES_BUDGET_BYTES"), os.environ.get("MCR_SERIES_SWEEP"))
+        if ckey is not None and ckey in cache:
+            return cache[ckey]
         sizes = {"traj": 8 * n * T, "real": 8 * n * T, "wr": 8 * n * R}
         free_bytes, _ = torch.cuda.mem_get_info(self._torch_device())
         budget = int(0.7 * free_bytes)
@@ -554,6 +560,8 @@ class RetirementMonteCarloSimulator:
             cur.append(name)
             used += sizes[name]
         plan.append(tuple(cur))
+        if ckey is not None:
+            cache[ckey] = plan
         return plan
 
     def _select(self, specs, out16, counts=None, stepwise: bool = False):
@@ -708,12 +716,26 @@ class RetirementMonteCarloSimulator:
         caller looping over batches gets the HBM-bound reductions of batch i underneath the
         issue-bound timeline kernel of batch i+1; the result then carries a `ready` event that
         `to_host()` / `wait()` honour."""
+        import torch
+
+        n_global = int(num_simulations)
+        try:
+            return self._aggregates_device(working_months, n_global, bands, first_path, timeline_events, samples, pipeline)
+        except torch.cuda.OutOfMemoryError:
+            # the cached series plan was made when more memory was free: plan again (single GPU only — ranks
+            # of a sharded run must keep identical plans, they agreed on the minimum over ranks up front)
+            if self._shard(n_global) != (0, n_global) or not self.__dict__.get("_plan_cache"):
+                raise
+            self._plan_cache.clear()
+            self._last_batch = None
+            torch.cuda.empty_cache()
+            return self._aggregates_device(working_months, n_global, bands, first_path, timeline_events, samples, pipeline)
+
+    def _aggregates_device(self, working_months, n_global, bands, first_path, timeline_events, samples, pipeline):
         import contextlib
 
         import torch
 
-        ctx = self.native_context
-        n_global = int(num_simulations)
         offset, n = self._shard(n_global)  # single GPU: (0, n_global)
         plan = self._series_plan(n, self._trajectory_len(int(working_months)), self.params_model.retirement_years,
                                  bool(bands), key=(int(working_months), n_global, bool(bands)))
