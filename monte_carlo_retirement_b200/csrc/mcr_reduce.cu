@@ -81,12 +81,13 @@ struct SelRow {
   uint64_t fbase;                   // first digit pass of an adaptive row: bin = (key >> fshift) - fbase
   uint64_t omin, omax;              // extreme keys seen OUTSIDE the window by the first digit pass (this GPU's elements)
   uint64_t fixed_key[kMaxTargets];  // per target of fixed_mask: its key
-  uint32_t fixed_mask;              // targets resolved by the first digit pass itself (see advance_row)
+  uint32_t fixed_mask;              // targets resolved by the first digit pass itself (see advance_row) ...
+  uint32_t omin_mask, omax_mask;    // ... of which: the row's minimum / maximum, i.e. omin / omax once those are final
   int32_t fshift;                   //   (64: no window — nothing sampled, or the row restarted from bit 0)
   int32_t cap;                      // candidate list capacity of this call (kCandCap; kPoolCap when ranks pool lists)
   int32_t whole;                    // the row is complete on this GPU (single-GPU call): omin / omax are the row's
   uint32_t done;                    // CTAs of the current scan that have finished this row (fused launches, see k_sel_hist)
-  uint32_t pad1;
+  uint32_t pad1, pad2, pad3;
   int64_t n_valid;
   int32_t n_groups;
   int32_t rb;                       // resolved bits (64 == done)
@@ -144,7 +145,7 @@ __global__ void k_sel_init(SelRow* __restrict__ rows, uint32_t* __restrict__ his
     R.n_groups = 1; R.n_valid = 0; R.n_cand = 0; R.overflow = 0; R.collected = 0; R.rb = 0;
     R.kmin = ~0ull; R.kmax = 0ull; R.adaptive = adaptive; R.fused = fused != 0; R.ready = 0; R.fixed_mask = 0;
     R.fbase = 0; R.fshift = 64; R.cap = (fused & 2) ? kPoolCap : kCandCap;
-    R.omin = ~0ull; R.omax = 0ull; R.whole = fused == 1; R.done = 0;
+    R.omin = ~0ull; R.omax = 0ull; R.whole = fused == 1; R.done = 0; R.omin_mask = 0; R.omax_mask = 0;
   }
   if (threadIdx.x < kMaxTargets) { R.gmin[threadIdx.x] = ~0ull; R.gmax[threadIdx.x] = 0ull; }
 }
@@ -708,26 +709,27 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
             // ranks inside the prefix bucket. A target below it is +0.0 when its rank falls among the
             // zeros of the `below` mass (zero-padded failures: negative keys first, then the zeros,
             // then small positives); any other target outside the bucket restarts the row.
-            // ... except the row's own minimum / maximum when the whole row is on this GPU: the first
-            // digit pass tracked the extreme keys outside the window
-            uint32_t fixed = 0;
+            // ... except the row's own minimum / maximum: the first digit pass tracked the extreme keys
+            // outside the window (omin / omax; with path shards on several GPUs they become global in the
+            // candidate exchange, before anything reads them — not in the plain stepwise protocol)
+            uint32_t fixed = 0, omin_m = 0, omax_m = 0;
             const int64_t nv = R.n_valid;
             for (int t = 0; t < nt; ++t) {
               if (nv > 0) {
                 const int64_t r = R.rank[t];
                 if (r < below) {
                   if (r >= below_neg && r < below_neg + below_zero) { fixed |= 1u << t; R.fixed_key[t] = kZeroKey; }
-                  else if (R.whole && r == 0) { fixed |= 1u << t; R.fixed_key[t] = R.omin; }
+                  else if (R.fused && r == 0) { fixed |= 1u << t; omin_m |= 1u << t; }
                   else s_restart = 1;
                 } else if (r >= below + part) {
-                  if (R.whole && r == nv - 1) { fixed |= 1u << t; R.fixed_key[t] = R.omax; }
+                  if (R.fused && r == nv - 1) { fixed |= 1u << t; omax_m |= 1u << t; }
                   else s_restart = 1;
                 }
               }
               R.rank[t] -= below;
             }
             if (s_restart) {
-              fixed = 0;
+              fixed = omin_m = omax_m = 0;
               for (int t = 0; t < nt; ++t) { R.rank[t] += below; R.prefix[t] = 0; R.group[t] = 0; R.bcount[t] = R.n_valid; }
             } else if (fixed) {
               // a fixed target shadows a live one from here on (same bucket walk, no group of its own):
@@ -743,6 +745,8 @@ __device__ __forceinline__ void advance_row(SelRow& R, uint32_t* H, int pass) {
               }
             }
             R.fixed_mask = fixed;
+            R.omin_mask = omin_m;
+            R.omax_mask = omax_m;
           }
         }
       }
@@ -949,8 +953,13 @@ __device__ __forceinline__ double finish_value(const SelRow& R, int k) {
   const int64_t nv = R.n_valid;
   if (nv <= 0) return CUDART_NAN;
   const int sa = R.slot[2 * k], sb = R.slot[2 * k + 1];
-  const double a = value_of(((R.fixed_mask >> sa) & 1u) ? R.fixed_key[sa] : R.prefix[sa]);
-  const double b = value_of(((R.fixed_mask >> sb) & 1u) ? R.fixed_key[sb] : R.prefix[sb]);
+  auto key_at = [&](int t) -> uint64_t {
+    if ((R.omin_mask >> t) & 1u) return R.omin;
+    if ((R.omax_mask >> t) & 1u) return R.omax;
+    return ((R.fixed_mask >> t) & 1u) ? R.fixed_key[t] : R.prefix[t];
+  };
+  const double a = value_of(key_at(sa));
+  const double b = value_of(key_at(sb));
   if (spec.median == 2) return a;
   if (spec.median) return (nv & 1) ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
   const double q = spec.q[k];
@@ -1035,14 +1044,14 @@ __global__ void __launch_bounds__(kTailThreads) k_sel_tail(SelRow* __restrict__ 
 // small by then (the rows stopped scanning because the GLOBAL histogram said they fit the
 // list), so instead of more all-reduced digit passes the ranks pool the candidates and each
 // finishes every row with the single-GPU tail. The exchange buffer is one int64 array
-//   xbuf = [ unresolved | counts[world][rows] | group extremes[rows][kMaxTargets][2] | pool[rows][kPoolCap] ]
+//   xbuf = [ unresolved | counts[world][rows] | extremes[rows][kMaxTargets + 1][2] (groups, then the row's omin / omax) | pool[rows][kPoolCap] ]
 // whose regions are combined by plain all-reduces: SUM of the counts (each rank fills only its
 // own line), MIN of the encoded extremes (as k_sel_extremes), SUM of the pool (each rank writes
 // its candidates, as bit patterns, at its own offset into zeros).
 __host__ __device__ inline size_t xbuf_counts_at() { return 1; }
 __host__ __device__ inline size_t xbuf_extremes_at(int rows, int world) { return 1 + (size_t)world * rows; }
 __host__ __device__ inline size_t xbuf_pool_at(int rows, int world) {
-  return xbuf_extremes_at(rows, world) + (size_t)rows * kMaxTargets * 2;
+  return xbuf_extremes_at(rows, world) + (size_t)rows * (kMaxTargets + 1) * 2;
 }
 
 __global__ void k_sel_export(SelRow* __restrict__ rows, long long* __restrict__ xbuf, int n_rows, int rank, int world) {
@@ -1055,10 +1064,14 @@ __global__ void k_sel_export(SelRow* __restrict__ rows, long long* __restrict__ 
     if (q == rank && R.rb < 64) c = R.overflow ? (long long)kPoolCap + 1 : (long long)R.n_cand;
     xbuf[xbuf_counts_at() + (size_t)q * n_rows + r] = c;
   }
-  long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * kMaxTargets * 2;
+  long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * (kMaxTargets + 1) * 2;
   for (int g = threadIdx.x; g < kMaxTargets; g += blockDim.x) {
     e[2 * g] = (long long)(R.gmin[g] ^ top);
     e[2 * g + 1] = (long long)((~R.gmax[g]) ^ top);
+  }
+  if (threadIdx.x == 0) {   // this rank's extreme keys outside the first digit window (finished rows too)
+    e[2 * kMaxTargets] = (long long)(R.omin ^ top);
+    e[2 * kMaxTargets + 1] = (long long)((~R.omax) ^ top);
   }
 }
 
@@ -1067,8 +1080,13 @@ __global__ void k_sel_place(SelRow* __restrict__ rows, const double* __restrict_
   __shared__ long long s_off, s_total;
   const int r = blockIdx.x;
   SelRow& R = rows[r];
-  if (R.rb >= 64) return;
   const unsigned long long top = 0x8000000000000000ull;
+  if (threadIdx.x == 0) {   // the GLOBAL omin / omax (a requested minimum / maximum may be all a finished row waits for)
+    const long long* eo = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * (kMaxTargets + 1) * 2 + 2 * kMaxTargets;
+    R.omin = (unsigned long long)eo[0] ^ top;
+    R.omax = ~((unsigned long long)eo[1] ^ top);
+  }
+  if (R.rb >= 64) return;
   if (threadIdx.x == 0) {
     long long off = 0, total = 0;
     for (int q = 0; q < world; ++q) {
@@ -1086,7 +1104,7 @@ __global__ void k_sel_place(SelRow* __restrict__ rows, const double* __restrict_
     const double* __restrict__ c = cand + (size_t)r * kCandCap;
     for (int i = threadIdx.x; i < mine; i += blockDim.x) pool[off + i] = __double_as_longlong(c[i]);
   }
-  const long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * kMaxTargets * 2;
+  const long long* e = xbuf + xbuf_extremes_at(n_rows, world) + (size_t)r * (kMaxTargets + 1) * 2;
   __syncthreads();
   if (threadIdx.x < kMaxTargets) {
     R.gmin[threadIdx.x] = (unsigned long long)e[2 * threadIdx.x] ^ top;

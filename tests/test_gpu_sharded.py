@@ -175,6 +175,33 @@ def test_pooled_tail_finishes_rows_with_a_mass_of_zeros():
         assert np.array_equal(o.cpu().numpy(), want, equal_nan=True)
 
 
+def test_pooled_tail_resolves_requested_minima_and_maxima():
+    """MCR_SEL_MINMAX rows (the histogram ranges of a step) over three logical ranks whose shards are long
+    enough to be SAMPLED for the first digit window: the true extremes sit where no sample looks, the
+    ranks exchange the extreme keys they saw outside the window with the candidate pool, and every rank
+    ends with the exact global minimum and maximum — no fallback."""
+    import torch
+
+    splits = (200_000, 150_001, 180_000)
+    n = sum(splits)
+    rng = np.random.default_rng(12)
+    x = np.exp(rng.normal(15, 0.7, (4, n)))
+    x[0, 30_000], x[0, 250_000] = 3.5, 9.9e11            # far outside the bulk, in pieces the sample skips
+    x[1, 20_000 + np.arange(5)] = -np.arange(1.0, 6.0)   # negative minimum next to a mass of zeros
+    x[1, rng.random(n) < 0.2] = 0.0
+    x[2] = 4.0                                           # constant row
+    x[3, rng.random(n) < 0.4] = np.nan                   # NaN are skipped
+    x[3, 401_000] = 1e-9
+    sim = make_sim(scenarios.TEST_BASE)
+    bounds = np.cumsum((0,) + splits)
+    shards = [torch.from_numpy(np.ascontiguousarray(x[:, a:b])).to("cuda") for a, b in zip(bounds, bounds[1:])]
+    outs, cnts, unresolved = _logical_pooled_quantiles(sim.native_context, shards, 4, [0.0, 1.0], median="minmax")
+    assert unresolved == 0
+    want = np.stack([np.nanmin(x, axis=1), np.nanmax(x, axis=1)], axis=1)
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), want)
+
+
 def test_pooled_tail_reports_rows_it_cannot_finish():
     """A dense cluster of distinct values inside a wide key range stays too big for the pool after
     all full passes: every rank reports the row, the caller falls back to the stepwise protocol."""
