@@ -918,10 +918,11 @@ __device__ __forceinline__ bool last_cta_of_row(SelRow& R) {
 // last CTA to finish a row walks the row's merged histogram right away (advance_row), while the other rows
 // are still being scanned; no separate advance launch, and its serial part stays off the critical path.
 __global__ void __launch_bounds__(kHistThreads) k_sel_hist(SelRow* __restrict__ rows, uint32_t* __restrict__ hist,
-                                                           const double* __restrict__ cand, int pass, int chunk,
-                                                           int stride, int fuse) {
-  extern __shared__ uint32_t sh[];  // [n_groups][256] or the kFirstWords of the first digit pass
-  __shared__ SelRow s_row;
+                                                              const double* __restrict__ cand, int pass, int chunk,
+                                                              int stride, int fuse) {
+  extern __shared__ __align__(16) uint32_t sh[];  // [n_groups][256] or the kFirstWords of the first digit pass
+  static_assert(sizeof(SelRow) <= sizeof(uint32_t) * kHistWords, "the staged row reuses the histogram's shared memory");
+  SelRow& s_row = *reinterpret_cast<SelRow*>(sh);   // (after the scan: 6 CTAs of 32 KB + tables per SM, no room to spare)
   SelRow& R = rows[blockIdx.y];
   if (R.rb >= 64 || R.ready) return;   // the whole grid line of the row returns here: nothing to advance
   uint32_t* H = hist + (size_t)blockIdx.y * kHistWords;
