@@ -208,27 +208,36 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
         T, R = b.T, b.R
         years.record_stream(copy_stream)
 
-        # ---- global bands (one distributed multi-row select) and the sample paths
-        bands = torch.empty((T, nq), **f64)
-        real_bands = torch.empty((T, nq), **f64)
-        wr_bands = torch.empty((R, nw), **f64)
+        # ---- global bands (one distributed multi-row select) and the sample paths, in ONE small block:
+        # ---- [bands | real bands | WR bands | samples (2 x k x T) | WR counts | select flag]
+        k = len(self._sample_columns(n_global))
+        sizes = (T * nq, T * nq, R * nw, 2 * k * T, R, 1)
+        small = torch.empty(sum(sizes), **f64)
+        at, parts = 0, []
+        for m in sizes:
+            parts.append(small[at:at + m])
+            at += m
+        bands, real_bands, wr_bands = parts[0].view(T, nq), parts[1].view(T, nq), parts[2].view(R, nw)
+        samples = parts[3].view(2, k, T)
         wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
         flag = self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
-        k = len(self._sample_columns(n_global))
-        samples = torch.zeros((2, k, T), **f64)   # each rank fills the columns it owns, summed into zeros
+        parts[3].zero_()                                # each rank fills the columns it owns, summed into zeros
         self._gather_samples(b.traj, n, T, lo, n_global, samples[0])
         self._gather_samples(b.real, n, T, lo, n_global, samples[1])
-        self._reduce_samples(samples)
-        if flag is not None and int(flag.item()) != 0:   # rare: the pooled select gave up on a row -> stepwise protocol
-            self.select_fallbacks += 1
-            self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts, stepwise=True)
-        s = samples.cpu().numpy()                       # synchronises the main stream
-        small = [bands.cpu().numpy(), wr_bands.cpu().numpy(), real_bands.cpu().numpy(), wr_counts.cpu().numpy()]
-        copy_stream.synchronize()
-        coll.barrier()                                  # every shard has landed in the shared block
-        self.last_d2h_bytes = n * (6 * 8 + 1) + (2 * T * nq + R * nw + 2 * k * T + R) * 8
-        # views of the block keep its generation busy on this rank (is_free): rank 0 all rows, the
-        # others the rows of their own shard
+        self._reduce_samples(parts[3])
+        parts[4].copy_(wr_counts)                       # (exact in float64)
+        if flag is None:
+            parts[5].zero_()
+        else:
+            parts[5].copy_(flag)
+        host_small = torch.empty(small.numel(), dtype=torch.float64, pin_memory=True)
+        host_small.copy_(small, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.last_d2h_bytes = n * (6 * 8 + 1) + (small.numel() - 1) * 8
+        # The frames wrap host memory the GPUs are still filling; they are built while the GPUs work and handed
+        # out after every shard has landed. Views of the block keep its generation busy on this rank
+        # (is_free): rank 0 all rows, the others the rows of their own shard.
         if coll.rank == 0:
             c, succ = block.np_cols, block.np_succ
         else:
@@ -242,14 +251,24 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
             "First Year Real Gross Withdrawal": c[3],
             "Inflation At Retirement": c[4],
         }, copy=False)
+        h = host_small.numpy()
+        o = [0]
+        for m in sizes:
+            o.append(o[-1] + m)
+        traj_pct = pd.DataFrame(h[o[0]:o[1]].reshape(T, nq), columns=TRAJECTORY_QUANTILES, copy=False)
+        real_pct = pd.DataFrame(h[o[1]:o[2]].reshape(T, nq), columns=TRAJECTORY_QUANTILES, copy=False)
+        wr_pct = pd.DataFrame(h[o[2]:o[3]].reshape(R, nw), columns=WITHDRAWAL_RATE_QUANTILES, copy=False)
+        done.synchronize()
+        if h[o[5]] != 0.0:   # rare: the pooled select gave up on a row -> stepwise protocol, block copied again
+            self.select_fallbacks += 1
+            self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts, stepwise=True)
+            parts[4].copy_(wr_counts)
+            host_small.copy_(small)
+        copy_stream.synchronize()
+        coll.barrier()                                  # every shard has landed in the shared block
+        s2 = h[o[3]:o[4]].reshape(2, k, T)
         self._last_batch = b
-        return (summary_df,
-                pd.DataFrame(small[0], columns=TRAJECTORY_QUANTILES),
-                s[0].tolist(),
-                pd.DataFrame(small[1], columns=WITHDRAWAL_RATE_QUANTILES),
-                pd.DataFrame(small[2], columns=TRAJECTORY_QUANTILES),
-                s[1].tolist(),
-                [int(v) for v in small[3]])
+        return (summary_df, traj_pct, s2[0].tolist(), wr_pct, real_pct, s2[1].tolist(), [int(v) for v in h[o[4]:o[5]]])
 
     def _staging(self, n: int, dev):
         if getattr(self, "_copy_stream", None) is None:

@@ -296,6 +296,7 @@ class RetirementMonteCarloSimulator:
         # host-returning batch calls split the timeline launch so that the device-to-host copy of the
         # summary columns overlaps the simulation (run_batch_device(chunks=...))
         self.e2e_chunks = int(os.environ.get("MCR_E2E_CHUNKS", "2"))
+        self.e2e_first_fraction = float(os.environ.get("MCR_E2E_FIRST_FRACTION", "0.7"))
         self._ctx: Optional[native.Context] = None
         self.last_search_stats: Dict[str, Any] = {}
         logger.info(f"Simulator initialized for scenario '{p.Nickname}' with main seed: {self.main_seed}")
@@ -418,7 +419,8 @@ class RetirementMonteCarloSimulator:
 
     def run_batch_device(self, working_months: int, num_simulations: int, *, first_path: int = 0,
                          series: bool = True, shocks=None, _fast_replay: bool = False,
-                         _small_returns: bool = False, on_chunk=None, chunks: int = 1) -> DeviceBatch:
+                         _small_returns: bool = False, on_chunk=None, chunks: int = 1,
+                         first_fraction: Optional[float] = None) -> DeviceBatch:
         """One launch of the timeline kernel for `num_simulations` paths; everything stays in HBM.
         `shocks` (device tensor [n_months, 3, n]) forces replay of those draws (strict build;
         `_fast_replay` / `_small_returns` are the tests' handles on the fast build and on its
@@ -487,8 +489,11 @@ class RetirementMonteCarloSimulator:
             return batch
         # contiguous path ranges, multiples of 1024 paths (whole CTAs, 128-byte-aligned rows)
         step = (-(-n // chunks) + 1023) // 1024 * 1024
-        for lo in range(0, n, step):
-            cnt = min(step, n - lo)
+        starts = list(range(0, n, step))
+        if chunks == 2 and first_fraction is not None:   # uneven halves: the LAST chunk's copy is the exposed one
+            starts = [0, min(n - 1024, max(1024, int(n * float(first_fraction)) // 1024 * 1024))]
+        for i, lo in enumerate(starts):
+            cnt = (starts[i + 1] if i + 1 < len(starts) else n) - lo
             part = native.Outputs()
             for name, t, width in (("start_balance", cols[0], 8), ("final_balance", cols[1], 8),
                                    ("first_year_gross", cols[2], 8), ("first_year_real", cols[3], 8),
@@ -648,30 +653,35 @@ class RetirementMonteCarloSimulator:
                 stage["cols"][5, lo:lo + cnt].copy_(years[lo:lo + cnt], non_blocking=True)
                 stage["succ"][lo:lo + cnt].copy_(b.success[lo:lo + cnt], non_blocking=True)
 
-        b = self.run_batch_device(working_months, n, series=True, on_chunk=copy_out, chunks=self.e2e_chunks)
+        b = self.run_batch_device(working_months, n, series=True, on_chunk=copy_out, chunks=self.e2e_chunks,
+                                  first_fraction=self.e2e_first_fraction)
         T, R = b.T, b.R
         nq, nw = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES)
         sample_cols = self._sample_columns(n)
         k = len(sample_cols)
         years.record_stream(stage["stream"])
 
-        # one small result block: bands (T*7 *2), WR bands (R*5), samples (k*T *2)
-        small = torch.empty(2 * T * nq + R * nw + 2 * k * T, dtype=torch.float64, device=dev)
+        # one small result block: bands (T*7 *2), WR bands (R*5), samples (k*T *2), WR observation counts (R)
+        small = torch.empty(2 * T * nq + R * nw + 2 * k * T + R, dtype=torch.float64, device=dev)
         o = 0
         bands = small[o:o + T * nq]; o += T * nq
         real_bands = small[o:o + T * nq]; o += T * nq
         wr_bands = small[o:o + R * nw]; o += R * nw
         samples = small[o:o + k * T]; o += k * T
-        real_samples = small[o:o + k * T]
+        real_samples = small[o:o + k * T]; o += k * T
         wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
         self._band_quantiles(b, bands, real_bands, wr_bands, wr_counts)
         ctx.gather_columns(b.traj, n, T, sample_cols, samples)
         ctx.gather_columns(b.real, n, T, sample_cols, real_samples)
-        host_small = small.cpu()          # synchronises the main stream
-        host_counts = wr_counts.cpu()
-        stage["stream"].synchronize()
-        self.last_d2h_bytes = n * (6 * 8 + 1) + host_small.numel() * 8 + R * 8
+        small[o:o + R].copy_(wr_counts)          # (exact in float64) — one block, one copy, one wait
+        host_small = torch.empty(small.numel(), dtype=torch.float64, pin_memory=True)
+        host_small.copy_(small, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.last_d2h_bytes = n * (6 * 8 + 1) + host_small.numel() * 8
 
+        # The frames below wrap page-locked host memory that the GPU is still filling: they are built while it
+        # works (nothing here reads a value), and handed out only after both streams have drained.
         c = stage["cols"].numpy()  # pinned block owned by this call's result (no copy)
         summary_df = pd.DataFrame({
             "Start Balance": c[0],
@@ -682,14 +692,16 @@ class RetirementMonteCarloSimulator:
             "First Year Real Gross Withdrawal": c[3],
             "Inflation At Retirement": c[4],
         }, copy=False)
-        s = host_small.numpy()
+        s = host_small.numpy()      # (the frames keep this call's pinned block alive)
         o = 0
-        traj_pct = pd.DataFrame(s[o:o + T * nq].reshape(T, nq).copy(), columns=TRAJECTORY_QUANTILES); o += T * nq
-        real_pct = pd.DataFrame(s[o:o + T * nq].reshape(T, nq).copy(), columns=TRAJECTORY_QUANTILES); o += T * nq
-        wr_pct = pd.DataFrame(s[o:o + R * nw].reshape(R, nw).copy(), columns=WITHDRAWAL_RATE_QUANTILES); o += R * nw
+        traj_pct = pd.DataFrame(s[o:o + T * nq].reshape(T, nq), columns=TRAJECTORY_QUANTILES, copy=False); o += T * nq
+        real_pct = pd.DataFrame(s[o:o + T * nq].reshape(T, nq), columns=TRAJECTORY_QUANTILES, copy=False); o += T * nq
+        wr_pct = pd.DataFrame(s[o:o + R * nw].reshape(R, nw), columns=WITHDRAWAL_RATE_QUANTILES, copy=False); o += R * nw
+        done.synchronize()
+        stage["stream"].synchronize()
         sample_list = s[o:o + k * T].reshape(k, T).tolist(); o += k * T
-        real_sample_list = s[o:o + k * T].reshape(k, T).tolist()
-        wr_observation_counts = [int(v) for v in host_counts.numpy()]
+        real_sample_list = s[o:o + k * T].reshape(k, T).tolist(); o += k * T
+        wr_observation_counts = [int(v) for v in s[o:o + R]]
         self.last_executed_months = None  # read lazily: b.counters[1]
         self._last_batch = b
         return (summary_df, traj_pct, sample_list, wr_pct, real_pct, real_sample_list, wr_observation_counts)
