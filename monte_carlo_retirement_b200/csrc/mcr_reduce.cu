@@ -3,12 +3,14 @@
 // 1045-1118, :78-96; backend/server.py:439-461,525-532; backend/plotting.py:46-59;
 // frontend/src/components/HistogramChart.jsx:13-60).
 //
-//   k_sel_*       exact order statistics by MSD radix select (8-bit digits on the
-//                 order-preserving 64-bit key): per pass one grid-wide histogram kernel
-//                 (rows x chunks CTAs, every requested quantile of a row resolved in the same
-//                 scan) + one tiny advance kernel; followed by numpy's 'linear' lerp
-//                 (numpy/lib/_function_base_impl.py: _QuantileMethods['linear'], _get_indexes,
-//                 _lerp) or the even/odd median rule of np.median.
+//   k_sel_*       exact order statistics by MSD radix select on the order-preserving 64-bit key:
+//                 a sampled look at every row, ONE scan that histograms ~8 K equal bins laid over
+//                 the sampled key range (every requested quantile of every row in the same
+//                 scan), 8-bit digit scans for the rows that need more, a gather scan and a tail
+//                 that walks the remaining digits on the gathered list; followed by numpy's
+//                 'linear' lerp (numpy/lib/_function_base_impl.py: _QuantileMethods['linear'],
+//                 _get_indexes, _lerp), the even/odd median rule of np.median, or the plain
+//                 minimum / maximum.
 //   k_rates       first-year withdrawal rates (simulation.py:92-95)
 //   k_minmax / k_histogram   cohort min/max and equal-width histograms with numpy.histogram
 //                 or frontend floor binning
@@ -45,25 +47,27 @@ __device__ __forceinline__ double value_of(uint64_t k) {
 // Per-row selection state, resident in the context's scratch between the passes of one call.
 //
 // MSD radix select on the order-preserving 64-bit key. A pass = one grid-wide histogram kernel
-// (rows x 16 K-element chunks, every requested quantile of a row resolved in the same scan,
-// merged into hist[row]) + one small "advance" step that walks each target's bucket to the
-// digit holding its rank. Two things keep the number of FULL scans of a row at 3-4:
-//   * adaptive start: pass 0 only counts the valid elements and reduces the row's min/max key;
-//     all keys share the leading clz(min ^ max) bits, so those are resolved for free and the
-//     8-bit digits of the following passes start at the first bit that actually discriminates.
-//     A constant row is finished after pass 0; a tightly concentrated row (early accumulation
-//     years) is as cheap as a wide one;
+// (rows x chunks CTAs, every requested quantile of a row resolved in the same scan, merged into
+// hist[row]) + an "advance" step that walks each target's bucket to the bin holding its rank —
+// a kernel of its own in the multi-GPU protocol, the last CTA of the row's scan otherwise. What
+// keeps the number of FULL scans of a row at two (histogram + gather) for ordinary data:
+//   * adaptive start: pass 0 only looks at a sample of the row for its extreme keys (zeros
+//     aside); pass 1 lays kFirstBins equal bins over that range — ~13 bits resolved by one scan
+//     however the range sits in key space — and counts what falls outside exactly. A constant
+//     row is finished after pass 1; a tightly concentrated row (early accumulation years) is as
+//     cheap as a wide one;
 //   * collect + tail: as soon as the live buckets of a row fit its candidate list together
-//     (typically after two digit passes; three when zero-padded failures stretch the key
-//     range) the row stops scanning; one more scan gathers the elements that share a target's
-//     prefix into the list; one more kernel sorts that list in shared memory, reads every
-//     target off it and interpolates. A bucket that stays too big for the list but holds ONE
-//     repeated value (zero-padded failed paths) is recognised by its min == max; only a big
-//     bucket of distinct values after all full passes falls back to scanning the row.
+//     (after pass 1 for C3's 1e6-element rows; one or two 8-bit digit passes later for rows of
+//     1e8..1e9 elements or outlier-stretched ranges) the row stops scanning; one more scan gathers
+//     the elements that share a target's prefix into the list; the tail kernel walks the
+//     remaining digits on that list and interpolates. A bucket that stays too big for the list
+//     but holds ONE repeated value (zero-padded failed paths) is recognised by its min == max;
+//     only a big bucket of distinct values after all full passes falls back to scanning the row.
 // The per-pass split also lets a multi-GPU caller all-reduce hist[] between the two halves of
 // a pass and obtain exact GLOBAL order statistics without moving data; the row
 // extremes then take one all-reduce(MIN) of their own (k_sel_extremes), without which that
 // stepwise protocol falls back to fixed 8-bit digits from bit 0 (adaptive = 0).
+// (hist[row] holds [groups][256] bins in the digit passes and kFirstBins + 4 words in pass 1.)
 // Layout: hist[rows][kMaxTargets][256] u32 is its own contiguous array (the all-reduced
 // buffer); the rest of the state is SelRow[rows] followed by the candidate lists.
 struct SelRow {
