@@ -92,9 +92,8 @@ class ClockSampler:
         self.bits = 0
         self.stop_flag = threading.Event()
         self.thread = None
-        # NVML queries take driver locks the launching thread also needs: poll sparsely (the timed region of the
-        # default run is > 100 ms, so it still gets several samples)
-        self.period_s = float(os.environ.get("MCR_BENCH_SAMPLE_MS", "25")) / 1e3
+        # polling period (measured: 10 / 25 / 100 ms make no difference to the step time, profiles/README.md)
+        self.period_s = float(os.environ.get("MCR_BENCH_SAMPLE_MS", "10")) / 1e3
 
     def _nvml_handle(self):
         import pynvml
