@@ -328,6 +328,37 @@ def test_quantiles_whatever_the_first_digit_window_looks_like(n):
     assert np.array_equal(got_mm[:, 0], x[:, mask].min(axis=1)) and np.array_equal(got_mm[:, 1], x[:, mask].max(axis=1))
 
 
+def test_multi_row_select_with_empty_and_tiny_rows_next_to_long_ones():
+    """One launch sequence over rows of very different lengths — none, one element, a few, a long sampled
+    row, 18 targets in one row: every grid line of the fused scan kernels must count its CTAs correctly,
+    whether they had work or not."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    long_row = np.exp(rng.normal(11, 1.2, 700_003))
+    rows = [np.empty(0), np.array([3.25]), np.array([2.0, -1.0, 5.5]), long_row, rng.normal(0, 1, 40_000)]
+    q9 = [0.01, 0.05, 0.10, 0.25, 0.50, 0.75, 0.90, 0.95, 0.99]
+    sim = make_sim(scenarios.TEST_BASE)
+    ctx = sim.native_context
+    dev = [None if len(r) == 0 else _dev(r) for r in rows]
+    specs = [(d, len(r), None, q9, False) for d, r in zip(dev, rows)]
+    specs += [(dev[3], len(long_row), None, [0.5], True), (dev[3], len(long_row), None, [0.0, 1.0], "minmax"),
+              (None, 0, None, [0.0, 1.0], "minmax")]
+    out = torch.empty((len(specs), 16), dtype=torch.float64, device="cuda")
+    cnt = torch.empty(len(specs), dtype=torch.int64, device="cuda")
+    for _ in range(2):   # twice: the per-row arrival counters must be back at zero
+        out.fill_(-7.0)
+        ctx.quantiles_rows(ctx.select_rows(specs), out, counts=cnt)
+        got = out.cpu().numpy()
+        for i, r in enumerate(rows):
+            want = pd.Series(r).quantile(q9).to_numpy() if len(r) else np.full(9, np.nan)
+            assert np.array_equal(got[i, :9], want, equal_nan=True), i
+        assert got[5, 0] == np.median(long_row)
+        assert got[6, 0] == long_row.min() and got[6, 1] == long_row.max()
+        assert np.isnan(got[7, 0]) and np.isnan(got[7, 1])
+        assert cnt.cpu().tolist() == [0, 1, 3, len(long_row), 40_000, len(long_row), len(long_row), 0]
+
+
 def test_histograms_match_numpy_and_frontend_rule():
     import torch
 
