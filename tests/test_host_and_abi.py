@@ -107,6 +107,38 @@ def test_constructor_contract():
         load_config_from_json("/nonexistent.json")
 
 
+def test_series_plan_is_decided_once_per_call_shape(monkeypatch):
+    """cudaMemGetInfo takes tens of milliseconds while kernels run; a step must not ask for it again
+    (it starved the launch queue: one bench run in ten was host-bound). Env overrides and key=None re-plan."""
+    import torch
+
+    calls = []
+
+    def fake_mem_get_info(device=None):
+        calls.append(device)
+        return (int(8 * 1000 * 61 * 2.5 / 0.7), 0)   # room for two trajectory series and a bit
+
+    monkeypatch.setattr(torch.cuda, "mem_get_info", fake_mem_get_info)
+    monkeypatch.delenv("MCR_SERIES_BUDGET_BYTES", raising=False)
+    monkeypatch.delenv("MCR_SERIES_SWEEP", raising=False)
+    sim = RetirementMonteCarloSimulator(_cfg())
+    monkeypatch.setattr(sim, "_torch_device", lambda: "cuda:0")   # (no device here: only the planning logic runs)
+    key = (120, 1000, True)
+    plan = sim._series_plan(1000, 61, 40, True, key)
+    assert plan == [("traj", "real"), ("wr",)] and len(calls) == 1
+    for _ in range(5):
+        assert sim._series_plan(1000, 61, 40, True, key) is plan
+    assert len(calls) == 1
+    assert sim._series_plan(1000, 61, 40, False, key) == [()] and len(calls) == 1      # no bands: nothing to plan
+    monkeypatch.setenv("MCR_SERIES_SWEEP", "1")                                       # an override is part of the key
+    assert sim._series_plan(1000, 61, 40, True, key) == [("traj",), ("real",), ("wr",)] and len(calls) == 2
+    monkeypatch.delenv("MCR_SERIES_SWEEP")
+    assert sim._series_plan(1000, 61, 40, True, key) is plan and len(calls) == 2
+    sim._series_plan(1000, 61, 40, True, None)                                        # ad-hoc query: not cached
+    assert len(calls) == 3
+    assert sim._series_plan(2000, 61, 40, True, (120, 2000, True)) == [("traj",), ("real",), ("wr",)] and len(calls) == 4
+
+
 def test_seed_streams_and_numpy_draws_match_reference():
     """`_path_seeds` / `_draw_shock_path` keep the reference's numpy semantics (golden seeds)."""
     for name in ("config_json", "tax_heavy"):
