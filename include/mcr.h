@@ -353,6 +353,9 @@ int mcr_years_to_ruin(mcr_ctx* ctx, const int32_t* ruin_month_dev, int64_t n, do
 
 #define MCR_HIST_NUMPY 0 /* numpy.histogram / matplotlib plt.hist(bins=n) — plotting.py:46-59  */
 #define MCR_HIST_FLOOR 1 /* idx = min(floor((v-min)/width), n-1) — HistogramChart.jsx:13-60   */
+#define MCR_HIST_RAW_RANGE 0x100 /* OR into mode: range_dev holds min / max of the UNDIVIDED values (e.g. straight out
+                                  * of a MCR_SEL_MINMAX select row); the kernel divides them by `divisor` itself — the
+                                  * same IEEE division it applies to every element */
 
 /* min/max of (values / divisor) over the cohort mask (all when NULL) into minmax_dev[2]
  * (NaN, NaN when the cohort is empty). */

@@ -843,7 +843,8 @@ int mcr_histogram(mcr_ctx* ctx, const double* values_dev, const uint8_t* mask_de
   if (!ctx || !values_dev || !range_dev || !hist_dev) return fail(ctx, MCR_EINVAL, "null argument");
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (n < 0 || !(divisor > 0) || n_bins <= 0 || n_bins > 8192) return fail(ctx, MCR_EINVAL, "bad n / divisor / n_bins");
-  if (mode != MCR_HIST_NUMPY && mode != MCR_HIST_FLOOR) return fail(ctx, MCR_EINVAL, "bad histogram mode");
+  if ((mode & ~MCR_HIST_RAW_RANGE) != MCR_HIST_NUMPY && (mode & ~MCR_HIST_RAW_RANGE) != MCR_HIST_FLOOR)
+    return fail(ctx, MCR_EINVAL, "bad histogram mode");
   DeviceGuard g(ctx->device);
   if (!g.ok) return fail(ctx, MCR_ECUDA, "cudaSetDevice failed");
   MCR_CUDA(ctx, launch_histogram(values_dev, mask_dev, n, divisor, n_bins, mode, range_dev, hist_dev,

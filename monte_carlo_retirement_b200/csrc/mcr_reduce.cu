@@ -1197,6 +1197,11 @@ __global__ void k_histogram(const double* __restrict__ x, const uint8_t* __restr
   for (int k = threadIdx.x; k < n_bins; k += blockDim.x) sh[k] = 0;
   __syncthreads();
   double first = range[0], last = range[1];
+  if (mode & MCR_HIST_RAW_RANGE) {   // extremes of the undivided values: divide like every element below
+    first = __ddiv_rn(first, divisor);
+    last = __ddiv_rn(last, divisor);
+    mode &= ~MCR_HIST_RAW_RANGE;
+  }
   const bool empty = !(first == first);
   if (!empty) {
     if (mode == 0 && first == last) { first = __dsub_rn(first, 0.5); last = __dadd_rn(last, 0.5); }

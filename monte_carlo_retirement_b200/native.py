@@ -20,6 +20,7 @@ STREAM_FINAL = 1
 SEL_MEDIAN = 0x1
 SEL_MINMAX = 0x2  # specs: median="minmax"
 HIST_NUMPY = 0
+HIST_RAW_RANGE = 0x100  # range2 holds min / max of the undivided values
 HIST_FLOOR = 1
 E_INVAL = -1
 

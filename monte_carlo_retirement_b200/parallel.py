@@ -154,12 +154,10 @@ class ShardedSimulator(RetirementMonteCarloSimulator):
     def _reduce_samples(self, block):
         return self.coll.sum_(block)
 
-    def _final_balance_histograms(self, b, rng_m, rng_1, hists) -> None:
-        # (the ranges are GLOBAL already: min / max of the cohort come out of the distributed select)
-        ctx, coll, n = self.native_context, self.coll, b.n
-        ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
-        ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
-        coll.sum_(hists)
+    def _final_balance_histograms(self, b, rng_raw, hists) -> None:
+        # (the range is GLOBAL already: min / max of the cohort come out of the distributed select)
+        super()._final_balance_histograms(b, rng_raw, hists)
+        self.coll.sum_(hists)
 
     # ---- the reference's 7-tuple ------------------------------------------------------------------
     def run_monte_carlo_simulations(self, working_months: int, num_simulations: int):

@@ -212,12 +212,21 @@ class DeviceAggregates:
         b = self.batch
         n, T, R = int(getattr(self, "n_override", b.n)), b.T, b.R
         nq, nw, nf = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES), len(FINAL_BALANCE_QUANTILES)
-        small = self.small.cpu().numpy()
-        cnt = self.counts.cpu().numpy()
+        o16 = self.out16.cpu().numpy()          # [rows][16]: 3 medians, final quantiles, min / max, then the band rows
+        cnt = self.cnt_all.cpu().numpy()
         hists = self.hists.cpu().numpy()
         counters = b.counters.cpu().numpy()
+        rng_1 = o16[4, 0:2]
+        rng_m = rng_1 / 1e6                     # (IEEE division, as the histogram kernel's)
         out: Dict[str, Any] = {}
-        if self.band_block is not None:
+        B0 = getattr(self, "first_band_row", None)
+        if B0 is not None:
+            out["trajectory_bands"] = pd.DataFrame(o16[B0:B0 + T, :nq].copy(), columns=TRAJECTORY_QUANTILES)
+            out["real_trajectory_bands"] = pd.DataFrame(o16[B0 + T:B0 + 2 * T, :nq].copy(), columns=TRAJECTORY_QUANTILES)
+            out["withdrawal_rate_bands"] = pd.DataFrame(o16[B0 + 2 * T:B0 + 2 * T + R, :nw].copy(),
+                                                        columns=WITHDRAWAL_RATE_QUANTILES)
+            out["withdrawal_rate_counts"] = [int(v) for v in cnt[B0 + 2 * T:B0 + 2 * T + R]]
+        elif self.band_block is not None:       # series swept in several passes: bands gathered per pass
             blk = self.band_block.cpu().numpy()
             out["trajectory_bands"] = pd.DataFrame(blk[:T * nq].reshape(T, nq).copy(), columns=TRAJECTORY_QUANTILES)
             out["real_trajectory_bands"] = pd.DataFrame(blk[T * nq:2 * T * nq].reshape(T, nq).copy(),
@@ -236,14 +245,12 @@ class DeviceAggregates:
             "success_count": n_success,
             "success_probability": float(n_success / n * 100.0),
             "executed_path_months": int(counters[1]),
-            "median_first_year_withdrawal_rate": float(small[0]),
-            "median_start_balance": float(small[1]),
-            "median_final_balance_successful": float(small[2]) if cnt[2] > 0 else 0.0,
-            "final_balance_quantiles": dict(zip(FINAL_BALANCE_QUANTILES, (float(v) for v in small[3:3 + nf]))),
-            "final_balance_hist_musd_100": {"range": [float(v) for v in small[3 + nf:3 + nf + 2]],
-                                            "counts": hists[:100].tolist()},
-            "final_balance_hist_60": {"range": [float(v) for v in small[3 + nf + 2:3 + nf + 4]],
-                                      "counts": hists[100:].tolist()},
+            "median_first_year_withdrawal_rate": float(o16[0, 0]),
+            "median_start_balance": float(o16[1, 0]),
+            "median_final_balance_successful": float(o16[2, 0]) if cnt[2] > 0 else 0.0,
+            "final_balance_quantiles": dict(zip(FINAL_BALANCE_QUANTILES, (float(v) for v in o16[3, :nf]))),
+            "final_balance_hist_musd_100": {"range": [float(v) for v in rng_m], "counts": hists[:100].tolist()},
+            "final_balance_hist_60": {"range": [float(v) for v in rng_1], "counts": hists[100:].tolist()},
             "ruin_month_hist": counters[2:].tolist(),
         })
         return out
@@ -803,9 +810,6 @@ class RetirementMonteCarloSimulator:
         nq, nw, nf = len(TRAJECTORY_QUANTILES), len(WITHDRAWAL_RATE_QUANTILES), len(FINAL_BALANCE_QUANTILES)
         rates = torch.empty(n, **f64)
         ctx.first_year_rates(b.cols[0], b.cols[3], n, rates)
-        # small = [swr, median start, median final(successful)] + final quantiles + 2 ranges
-        small = torch.empty(3 + nf + 4, **f64)
-        cnt = torch.empty(3, dtype=torch.int64, device=dev)
         # every order statistic of the step in ONE multi-row select: 3 medians (different columns /
         # cohorts), the 9 final-balance quantiles and, when the series are resident, the bands
         # (row 4: min and max of the successful cohort's final balances — the ranges of the two histograms)
@@ -828,38 +832,25 @@ class RetirementMonteCarloSimulator:
                 self.select_fallbacks += 1
                 self._select(desc, out16, cnt_all, stepwise=True)
             flag = None
-        small[0:3].copy_(out16[0:3, 0])
-        cnt.copy_(cnt_all[0:3])
-        small[3:3 + nf].copy_(out16[3, :nf])
-        # histogram ranges: [min, max] in $M (plotting.py:46-59: final / 1e6 — a division by a positive
-        # constant is monotone, so min(x / 1e6) == min(x) / 1e6 bit for bit) and in $ (HistogramChart.jsx)
-        rng_m = small[3 + nf:3 + nf + 2]
-        rng_1 = small[3 + nf + 2:3 + nf + 4]
-        rng_1.copy_(out16[4, 0:2])
-        # (a DEVICE divisor: torch turns a division by a host scalar into a multiplication by its reciprocal,
-        # which is not the correctly rounded quotient the histogram kernel computes for every element)
-        if getattr(self, "_million", None) is None or self._million.device != dev:
-            self._million = torch.full((1,), 1e6, **f64)
-        torch.div(out16[4, 0:2], self._million, out=rng_m)
+        # Nothing is rearranged on the device: to_host() reads the medians, quantiles and bands straight out of the
+        # select's [rows][16] output. Histogram ranges: row 4 holds [min, max] of the successful final balances
+        # in $; the $M histogram (plotting.py:46-59: final / 1e6) lets the kernel divide them by 1e6 itself — a
+        # division by a positive constant is monotone, so min(x / 1e6) == min(x) / 1e6 bit for bit.
         hists = torch.zeros(160, dtype=torch.int64, device=dev)
-        self._final_balance_histograms(b, rng_m, rng_1, hists)
+        self._final_balance_histograms(b, out16[4, 0:2], hists)
         band_block = wr_counts = sample_block = None
         if bands and samples:
             sample_block = torch.zeros((2, len(self._sample_columns(n_global)), T), **f64)
         if bands:
-            band_block = torch.empty(2 * T * nq + R * nw, **f64)
-            wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
-            if with_bands:
+            if with_bands:                      # (the bands are rows B0.. of out16)
                 if sample_block is not None:
                     self._gather_samples(b.traj, n, T, offset, n_global, sample_block[0])
                     self._gather_samples(b.real, n, T, offset, n_global, sample_block[1])
-                band_block[:T * nq].view(T, nq).copy_(out16[B0:B0 + T, :nq])
-                band_block[T * nq:2 * T * nq].view(T, nq).copy_(out16[B0 + T:B0 + 2 * T, :nq])
-                band_block[2 * T * nq:].view(R, nw).copy_(out16[B0 + 2 * T:, :nw])
-                wr_counts.copy_(cnt_all[B0 + 2 * T:])
             else:
                 # the three series do not fit together: one multi-row select per pass of the plan;
                 # the first pass's series came with the summary batch, the others are recomputed
+                band_block = torch.empty(2 * T * nq + R * nw, **f64)
+                wr_counts = torch.empty(R, dtype=torch.int64, device=dev)
                 layout = {"traj": (T, TRAJECTORY_QUANTILES, 0), "real": (T, TRAJECTORY_QUANTILES, T * nq),
                           "wr": (R, WITHDRAWAL_RATE_QUANTILES, 2 * T * nq)}
                 for k, group in enumerate(plan):
@@ -897,19 +888,21 @@ class RetirementMonteCarloSimulator:
         self._last_batch = b
         if sample_block is not None:
             self._reduce_samples(sample_block)
-        agg = DeviceAggregates(batch=b, small=small, counts=cnt, hists=hists, band_block=band_block,
-                               wr_counts=wr_counts, rates=rates, sample_block=sample_block)
+        agg = DeviceAggregates(batch=b, out16=out16, cnt_all=cnt_all, first_band_row=(B0 if with_bands else None),
+                               hists=hists, band_block=band_block, wr_counts=wr_counts, rates=rates,
+                               sample_block=sample_block)
         agg.n_override = n_global
         agg.select_flag = flag
         return agg
 
-    def _final_balance_histograms(self, b: DeviceBatch, rng_m, rng_1, hists) -> None:
+    def _final_balance_histograms(self, b: DeviceBatch, rng_raw, hists) -> None:
         """100-bin numpy histogram in $M (plotting.py:46-59) and the dashboard's 60-bin floor
         histogram (HistogramChart.jsx:13-60) of the successful cohort's final balances."""
         ctx = self.native_context
         n = b.n
-        ctx.histogram(b.cols[1], n, 100, rng_m, hists[0:], mask=b.success, divisor=1e6, mode=native.HIST_NUMPY)
-        ctx.histogram(b.cols[1], n, 60, rng_1, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
+        ctx.histogram(b.cols[1], n, 100, rng_raw, hists[0:], mask=b.success, divisor=1e6,
+                      mode=native.HIST_NUMPY | native.HIST_RAW_RANGE)
+        ctx.histogram(b.cols[1], n, 60, rng_raw, hists[100:], mask=b.success, divisor=1.0, mode=native.HIST_FLOOR)
 
     def run_aggregates(self, working_months: int, num_simulations: int, *, bands: bool = True,
                        first_path: int = 0, samples: bool = False) -> Dict[str, Any]:
