@@ -51,6 +51,17 @@ def test_pod_layouts_match_the_header():
     assert C.sizeof(native.PathRecord) == 5 * 8 + 4 * 4
 
 
+def test_python_constants_match_the_header_macros():
+    header = open(os.path.join(ROOT, "include", "mcr.h")).read()
+    macros = {m.group(1): int(m.group(2).rstrip("uU"), 0)
+              for m in re.finditer(r"#define\s+(MCR_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+[uU]?|\d+[uU]?)\b", header)}
+    pairs = {"SEL_MEDIAN": "MCR_SEL_MEDIAN", "SEL_MINMAX": "MCR_SEL_MINMAX", "HIST_NUMPY": "MCR_HIST_NUMPY",
+             "HIST_FLOOR": "MCR_HIST_FLOOR", "HIST_RAW_RANGE": "MCR_HIST_RAW_RANGE"}
+    for py, c in pairs.items():
+        assert c in macros, c
+        assert getattr(native, py) == macros[c], (py, c)
+
+
 def test_host_side_abi_helpers_match_reference_known_answers():
     lib = native.load_library()
     z = golden_io.load_helpers()
